@@ -385,34 +385,54 @@ int orc_spawn(orc_env *e) {
 
 void orc_begin_tick(orc_env *e) { e->tick++; }
 
+void orc_encode(const orc_env *e, int i, int clip, int P, float *out);
+
 /* One pass of the while-loop body of Scene.run_mode (Scene.py:111-164) with a
  * built-in action source.  Per-AGV logs (length N): act[i] = action taken or -1
  * if AGV i took no turn, rew[i] (double), end[i], plen[i] = len(action_list) of
- * the policy BFS (or path_len_new when shaped).  Returns the number of turns
- * taken.  Sets e->over when run_mode would have returned. */
-int orc_tick(orc_env *e, int proto, int policy, const int8_t *given,
-             int8_t *act, double *rew, uint8_t *end, int *plen) {
-    if (e->over) { for (int i = 0; i < e->N; i++) { act[i] = -1; rew[i] = 0; end[i] = 0; plen[i] = 0; } return 0; }
+ * the policy BFS, slen[i] = rectify_reward's path_length_new or 0xFFFF.
+ * obs_kind 0 none / 1 clip [3,K,K] / 2 full [3,H,W]: obs (before the move, what
+ * choose_action sees) and next_obs (after, what store_info sees) per AGV, zeros
+ * for AGVs without a turn; either may be NULL.  A given action < 0 falls back to
+ * the guided policy.  Returns the number of turns taken.  Sets e->over when
+ * run_mode would have returned. */
+int orc_tick_obs(orc_env *e, int proto, int policy, const int8_t *given,
+                 int8_t *act, double *rew, uint8_t *end, int *plen, int *slen,
+                 int obs_kind, int P, float *obs, float *next_obs) {
+    int K = 2 * P + 1;
+    size_t R = obs_kind == 1 ? (size_t)3 * K * K : (obs_kind == 2 ? (size_t)3 * e->H * e->W : 0);
+    for (int i = 0; i < e->N; i++) { act[i] = -1; rew[i] = 0; end[i] = 0; plen[i] = 0; if (slen) slen[i] = 0xFFFF; }
+    if (obs && R) memset(obs, 0, sizeof(float) * R * e->N);
+    if (next_obs && R) memset(next_obs, 0, sizeof(float) * R * e->N);
+    if (e->over) return 0;
     int turns = 0;
     e->tick++;
-    for (int i = 0; i < e->N; i++) { act[i] = -1; rew[i] = 0; end[i] = 0; plen[i] = 0; }
     for (int i = 0; i < e->N; i++) {
         int st = orc_turn_state(e, i);
         if (st == -1) break;
         if (st == -2) { e->over = 1; return turns; }
         if (st == 0) continue;
+        if (obs && R) orc_encode(e, i, obs_kind == 1, P, obs + R * i);
         int a, l = 0;
-        if (policy == ORC_POLICY_GIVEN) a = given[i];
+        if (policy == ORC_POLICY_GIVEN && given[i] >= 0) a = given[i];
         else if (policy == ORC_POLICY_ASTAR) a = orc_action_astar(e, i, &l);
         else a = orc_action_guided(e, i, &l);
         int ri, ie, su, pl; double rf;
         orc_execute(e, i, a, proto, &ri, &rf, &ie, &su, &pl);
-        act[i] = (int8_t)a; rew[i] = rf; end[i] = (uint8_t)ie; plen[i] = su ? pl : l;
+        if (proto == ORC_PROTO_ASTAR) ie = 0; /* ignored by the loop, Scene.py:159-162 */
+        act[i] = (int8_t)a; rew[i] = rf; end[i] = (uint8_t)ie; plen[i] = l;
+        if (slen && su) slen[i] = pl;
+        if (next_obs && R) orc_encode(e, i, obs_kind == 1, P, next_obs + R * i);
         turns++;
         if (proto == ORC_PROTO_INTELLIGENT && ie) { e->over = 1; return turns; }
     }
     orc_spawn(e);
     return turns;
+}
+
+int orc_tick(orc_env *e, int proto, int policy, const int8_t *given,
+             int8_t *act, double *rew, uint8_t *end, int *plen) {
+    return orc_tick_obs(e, proto, policy, given, act, rew, end, plen, 0, 0, 0, 0, 0);
 }
 
 /* StateManager.create_state (StateManager.py:14-41) for AGV i of the current

@@ -62,6 +62,8 @@ def lib():
         L.orc_begin_tick.argtypes = [vp]
         L.orc_tick.restype = i
         L.orc_tick.argtypes = [vp, i, i, vp, vp, vp, vp, vp]
+        L.orc_tick_obs.restype = i
+        L.orc_tick_obs.argtypes = [vp, i, i, vp, vp, vp, vp, vp, vp, i, i, vp, vp]
         L.orc_encode.argtypes = [vp, i, i, i, vp]
         L.orc_snapshot.restype = i
         L.orc_snapshot.argtypes = [vp, vp]
@@ -222,6 +224,23 @@ class Env:
         n = lib().orc_tick(self._h, proto, policy, _p(g) if g is not None else None, _p(act), _p(rew), _p(end),
                            _p(plen))
         return n, act, rew, end, plen
+
+    def tick_obs(self, proto, policy, given=None, obs_kind=0, P=3, want_next=False):
+        """(turns, act, rew, end, plen, slen, obs, next_obs); obs are float32 [N,3,..]"""
+        act = np.zeros(self.N, dtype=np.int8)
+        rew = np.zeros(self.N, dtype=np.float64)
+        end = np.zeros(self.N, dtype=np.uint8)
+        plen = np.zeros(self.N, dtype=np.int32)
+        slen = np.zeros(self.N, dtype=np.int32)
+        K = 2 * P + 1
+        shp = None if obs_kind == 0 else ((self.N, 3, K, K) if obs_kind == 1 else (self.N, 3, self.H, self.W))
+        obs = np.zeros(shp, dtype=np.float32) if shp else None
+        nxt = np.zeros(shp, dtype=np.float32) if (shp and want_next) else None
+        g = np.ascontiguousarray(given, dtype=np.int8) if given is not None else None
+        n = lib().orc_tick_obs(self._h, proto, policy, _p(g) if g is not None else None, _p(act), _p(rew), _p(end),
+                               _p(plen), _p(slen), obs_kind, P, _p(obs) if obs is not None else None,
+                               _p(nxt) if nxt is not None else None)
+        return n, act, rew, end, plen, slen, obs, nxt
 
     def encode(self, i, clip=False, P=3):
         K = 2 * P + 1

@@ -1,0 +1,695 @@
+// agv_core.cuh -- warp-cooperative device core of the batched multi-AGV scene.
+//
+// One warp owns one scene (environment) for the duration of a kernel: the scene's
+// state block is staged in shared memory, the grid lives in registers as one bit
+// per cell (row r is owned by lane r / RPL, slot r % RPL, NW 64-bit words per
+// row), and the reference's turn order (Scene.py:124-162) is a sequential loop
+// inside the warp.  BFS ("A*", astar.py:73-153) is a bit-parallel, level-
+// synchronous frontier expansion: one level = 2 row shuffles + shifts/ORs, no
+// shared memory and no block barrier.
+//
+// Reference citations (file:line) are relative to
+// stoneMan349/Reinforcement-learning-for-multi-AGV-pathfinding.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace agv {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int A_UP = 0, A_RIGHT = 1, A_DOWN = 2, A_LEFT = 3, A_STOP = 4;
+constexpr int PROTO_ASTAR = 0, PROTO_INTELLIGENT = 1;
+constexpr int POLICY_GIVEN = 0, POLICY_ASTAR = 1, POLICY_GUIDED = 2;
+constexpr int OBS_NONE = 0, OBS_CLIP = 1, OBS_FULL = 2;
+constexpr uint16_t BF16_ONE = 0x3F80;
+constexpr int HDR_BYTES = 32;
+
+// Scene state header, first HDR_BYTES of a scene block.
+struct EnvHdr {
+    uint32_t tick;       // Scene.running_time
+    uint32_t cursor;     // len(layout.task_arrangement[0])
+    uint32_t n_done;     // sum(layout.task_arrangement[2])
+    uint16_t n_created;  // created AGVs are the prefix [0, n_created)
+    uint8_t finished;    // layout.task_finished
+    uint8_t over;        // run_mode has returned
+    uint64_t acted_mask; // AGVs that took a turn in the current tick (sub-step protocol)
+    uint64_t reserved;
+};
+static_assert(sizeof(EnvHdr) == HDR_BYTES, "header layout");
+
+struct DevCfg {
+    int H, W, E, N, T, P, K;
+    int always_loaded, always_empty, shaped, auto_reset;
+    long long max_steps;
+    int env_stride;                 // bytes per scene block (multiple of 16)
+    int off_pos, off_tgt, off_ord, off_meta;  // byte offsets of the per-AGV arrays
+    uint8_t *state;                 // [E * env_stride]
+    const uint32_t *tasks;          // [E * T] sx | sy<<8 | px<<16 | py<<24
+    const uint8_t *grid;            // [H * W] codes 0/1/2
+    const uint64_t *storage_rows;   // [H * NW] bit c of row r = storage station
+    const uint64_t *picking_rows;   // [H * NW]
+    const uint64_t *inb_rows;       // [H * NW] columns < W
+    unsigned long long *counters;   // [3] turns, episodes ended, invalid actions
+};
+
+// per-AGV meta byte: bits 0-1 task_stage, bit 2 loaded, bit 3 all_assigned (idle)
+struct Agv {
+    int x, y, tx, ty, stage, loaded, idle, order;
+};
+
+__device__ __forceinline__ int meta_pack(const Agv &a) {
+    return (a.stage & 3) | (a.loaded ? 4 : 0) | (a.idle ? 8 : 0);
+}
+
+// ------------------------------------------------------------------ bit rows
+template <int NW>
+struct Row {
+    uint64_t w[NW];
+};
+
+template <int NW>
+__device__ __forceinline__ Row<NW> rzero() {
+    Row<NW> r;
+#pragma unroll
+    for (int i = 0; i < NW; i++) r.w[i] = 0ull;
+    return r;
+}
+template <int NW>
+__device__ __forceinline__ Row<NW> ror(const Row<NW> &a, const Row<NW> &b) {
+    Row<NW> r;
+#pragma unroll
+    for (int i = 0; i < NW; i++) r.w[i] = a.w[i] | b.w[i];
+    return r;
+}
+template <int NW>
+__device__ __forceinline__ Row<NW> rand_(const Row<NW> &a, const Row<NW> &b) {
+    Row<NW> r;
+#pragma unroll
+    for (int i = 0; i < NW; i++) r.w[i] = a.w[i] & b.w[i];
+    return r;
+}
+template <int NW>
+__device__ __forceinline__ Row<NW> randn(const Row<NW> &a, const Row<NW> &b) {  // a & ~b
+    Row<NW> r;
+#pragma unroll
+    for (int i = 0; i < NW; i++) r.w[i] = a.w[i] & ~b.w[i];
+    return r;
+}
+template <int NW>
+__device__ __forceinline__ bool rany(const Row<NW> &a) {
+    uint64_t v = 0;
+#pragma unroll
+    for (int i = 0; i < NW; i++) v |= a.w[i];
+    return v != 0ull;
+}
+// column c+1 <- column c
+template <int NW>
+__device__ __forceinline__ Row<NW> rshl1(const Row<NW> &a) {
+    Row<NW> r;
+#pragma unroll
+    for (int i = NW - 1; i >= 0; i--) r.w[i] = (a.w[i] << 1) | (i > 0 ? (a.w[i - 1] >> 63) : 0ull);
+    return r;
+}
+template <int NW>
+__device__ __forceinline__ Row<NW> rshr1(const Row<NW> &a) {
+    Row<NW> r;
+#pragma unroll
+    for (int i = 0; i < NW; i++) r.w[i] = (a.w[i] >> 1) | (i + 1 < NW ? (a.w[i + 1] << 63) : 0ull);
+    return r;
+}
+template <int NW>
+__device__ __forceinline__ Row<NW> rshfl_up(const Row<NW> &a) {
+    Row<NW> r;
+#pragma unroll
+    for (int i = 0; i < NW; i++) r.w[i] = __shfl_up_sync(FULL, (unsigned long long)a.w[i], 1);
+    return r;
+}
+template <int NW>
+__device__ __forceinline__ Row<NW> rshfl_down(const Row<NW> &a) {
+    Row<NW> r;
+#pragma unroll
+    for (int i = 0; i < NW; i++) r.w[i] = __shfl_down_sync(FULL, (unsigned long long)a.w[i], 1);
+    return r;
+}
+
+// set bit (row r, col c) on the lane that owns row r
+template <int NW, int RPL>
+__device__ __forceinline__ void set_bit(Row<NW> (&rows)[RPL], int r, int c, int lane) {
+    const int ol = r / RPL, os = r % RPL;
+    const uint64_t bit = 1ull << (c & 63);
+    const int wi = c >> 6;
+#pragma unroll
+    for (int s = 0; s < RPL; s++)
+#pragma unroll
+        for (int i = 0; i < NW; i++)
+            if (lane == ol && s == os && i == wi) rows[s].w[i] |= bit;
+}
+template <int NW, int RPL>
+__device__ __forceinline__ void clear_bit(Row<NW> (&rows)[RPL], int r, int c, int lane) {
+    const int ol = r / RPL, os = r % RPL;
+    const uint64_t bit = 1ull << (c & 63);
+    const int wi = c >> 6;
+#pragma unroll
+    for (int s = 0; s < RPL; s++)
+#pragma unroll
+        for (int i = 0; i < NW; i++)
+            if (lane == ol && s == os && i == wi) rows[s].w[i] &= ~bit;
+}
+// true only on the owner lane, when the bit is set
+template <int NW, int RPL>
+__device__ __forceinline__ bool test_bit_local(const Row<NW> (&rows)[RPL], int r, int c, int lane) {
+    const int ol = r / RPL, os = r % RPL;
+    const int wi = c >> 6;
+    uint64_t v = 0;
+#pragma unroll
+    for (int s = 0; s < RPL; s++)
+#pragma unroll
+        for (int i = 0; i < NW; i++)
+            if (s == os && i == wi) v = rows[s].w[i];
+    return (lane == ol) && ((v >> (c & 63)) & 1ull);
+}
+
+// ------------------------------------------------------------------ BFS
+// Target-rooted bit-parallel BFS over `valid`; stops at the first level whose
+// frontier touches a neighbour of the start cell.  Equivalent to
+// FindPathAstar(valid, start, target).run_astar_method() (astar.py:66-153) as far
+// as its callers use it (Explorer.py:286-302, MADQN.py:192-200): returns
+// action_list[0] (STOP when not found or empty) and len(action_list) in `len`.
+// The reference's open list is FIFO (all_cost is never assigned, astar.py:14,86)
+// and re-parents on ties (astar.py:108-117), which makes the path the
+// lexicographically largest shortest path under LEFT < UP < DOWN < RIGHT
+// (neighbour order astar.py:33-38); hence the priority RIGHT, DOWN, UP, LEFT
+// among start neighbours one step closer to the target.
+// Coordinates are 0-based.  All lanes must call; the result is warp-uniform.
+template <int NW, int RPL>
+__device__ __forceinline__ int warp_bfs(const Row<NW> (&valid)[RPL], int sx, int sy, int tx, int ty, int H, int W,
+                                        int lane, int &len) {
+    len = 0;
+    if (sx == tx && sy == ty) return A_STOP;  // found, empty action list (astar.py:90-92)
+    Row<NW> f[RPL], vis[RPL], nb[RPL];
+#pragma unroll
+    for (int s = 0; s < RPL; s++) { f[s] = rzero<NW>(); nb[s] = rzero<NW>(); }
+    set_bit<NW, RPL>(f, ty, tx, lane);
+#pragma unroll
+    for (int s = 0; s < RPL; s++) { f[s] = rand_(f[s], valid[s]); vis[s] = f[s]; }
+    if (sx + 1 < W) set_bit<NW, RPL>(nb, sy, sx + 1, lane);
+    if (sy + 1 < H) set_bit<NW, RPL>(nb, sy + 1, sx, lane);
+    if (sy - 1 >= 0) set_bit<NW, RPL>(nb, sy - 1, sx, lane);
+    if (sx - 1 >= 0) set_bit<NW, RPL>(nb, sy, sx - 1, lane);
+    const int max_level = H * W;
+    for (int level = 0; level <= max_level; ++level) {
+        unsigned fl = 0;
+#pragma unroll
+        for (int s = 0; s < RPL; s++) {
+            fl |= rany(f[s]) ? 1u : 0u;
+            fl |= rany(rand_(f[s], nb[s])) ? 2u : 0u;
+        }
+        const unsigned red = __reduce_or_sync(FULL, fl);
+        if (red & 2u) {
+            unsigned code = 0;
+            if (sx + 1 < W && test_bit_local<NW, RPL>(f, sy, sx + 1, lane)) code |= 1u;
+            if (sy + 1 < H && test_bit_local<NW, RPL>(f, sy + 1, sx, lane)) code |= 2u;
+            if (sy - 1 >= 0 && test_bit_local<NW, RPL>(f, sy - 1, sx, lane)) code |= 4u;
+            if (sx - 1 >= 0 && test_bit_local<NW, RPL>(f, sy, sx - 1, lane)) code |= 8u;
+            code = __reduce_or_sync(FULL, code);
+            len = level + 1;
+            if (code & 1u) return A_RIGHT;
+            if (code & 2u) return A_DOWN;
+            if (code & 4u) return A_UP;
+            return A_LEFT;
+        }
+        if (!(red & 1u)) return A_STOP;  // frontier empty: target unreachable
+        Row<NW> up_in = rshfl_up(f[RPL - 1]);
+        Row<NW> dn_in = rshfl_down(f[0]);
+        if (lane == 0) up_in = rzero<NW>();
+        if (lane == 31) dn_in = rzero<NW>();
+        Row<NW> n[RPL];
+#pragma unroll
+        for (int s = 0; s < RPL; s++) {
+            Row<NW> a = ror(rshl1(f[s]), rshr1(f[s]));
+            Row<NW> u = (s > 0) ? f[s > 0 ? s - 1 : 0] : up_in;
+            Row<NW> d = (s < RPL - 1) ? f[s < RPL - 1 ? s + 1 : 0] : dn_in;
+            a = ror(a, ror(u, d));
+            n[s] = rand_(a, randn(valid[s], vis[s]));
+        }
+#pragma unroll
+        for (int s = 0; s < RPL; s++) { vis[s] = ror(vis[s], n[s]); f[s] = n[s]; }
+    }
+    return A_STOP;
+}
+
+// Full distance field from the target (uint16, 0xFFFF unreachable) into dist[H*W]
+// (global or shared).  Used by the host-side FindPathAstar mirror to rebuild
+// path_list / action_list.
+template <int NW, int RPL>
+__device__ __forceinline__ void warp_bfs_field(const Row<NW> (&valid)[RPL], int tx, int ty, int H, int W, int lane,
+                                               uint16_t *dist) {
+    for (int p = lane; p < H * W; p += 32) dist[p] = 0xFFFF;
+    __syncwarp();
+    Row<NW> f[RPL], vis[RPL];
+#pragma unroll
+    for (int s = 0; s < RPL; s++) f[s] = rzero<NW>();
+    set_bit<NW, RPL>(f, ty, tx, lane);
+#pragma unroll
+    for (int s = 0; s < RPL; s++) { f[s] = rand_(f[s], valid[s]); vis[s] = f[s]; }
+    for (int level = 0; level <= H * W; ++level) {
+        unsigned fl = 0;
+#pragma unroll
+        for (int s = 0; s < RPL; s++) {
+            fl |= rany(f[s]) ? 1u : 0u;
+            const int r = lane * RPL + s;
+#pragma unroll
+            for (int i = 0; i < NW; i++) {
+                uint64_t m = f[s].w[i];
+                while (m) {
+                    const int b = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    dist[r * W + i * 64 + b] = (uint16_t)level;
+                }
+            }
+        }
+        if (!__any_sync(FULL, fl != 0)) break;
+        Row<NW> up_in = rshfl_up(f[RPL - 1]);
+        Row<NW> dn_in = rshfl_down(f[0]);
+        if (lane == 0) up_in = rzero<NW>();
+        if (lane == 31) dn_in = rzero<NW>();
+        Row<NW> n[RPL];
+#pragma unroll
+        for (int s = 0; s < RPL; s++) {
+            Row<NW> a = ror(rshl1(f[s]), rshr1(f[s]));
+            Row<NW> u = (s > 0) ? f[s > 0 ? s - 1 : 0] : up_in;
+            Row<NW> d = (s < RPL - 1) ? f[s < RPL - 1 ? s + 1 : 0] : dn_in;
+            a = ror(a, ror(u, d));
+            n[s] = rand_(a, randn(valid[s], vis[s]));
+        }
+#pragma unroll
+        for (int s = 0; s < RPL; s++) { vis[s] = ror(vis[s], n[s]); f[s] = n[s]; }
+    }
+}
+
+// ------------------------------------------------------------------ scene in a warp
+template <int NW, int RPL>
+struct WarpScene {
+    const DevCfg &c;
+    int lane;
+    // scene block staged in shared memory
+    EnvHdr *hdr_s;
+    uint16_t *pos_s, *tgt_s, *ord_s;
+    uint8_t *meta_s;
+    uint64_t *vrow_s;  // [H * NW] scratch rows of the current valid matrix (for the encoder)
+    const uint32_t *tasks_e;
+    // warp-uniform copy of the header
+    uint32_t tick, cursor, n_done;
+    int n_created, finished, over;
+    uint64_t acted_mask;
+    // static layout rows + occupancy of created AGVs
+    Row<NW> stor[RPL], pick[RPL], inb[RPL], occ[RPL];
+
+    __device__ __forceinline__ WarpScene(const DevCfg &cfg, int lane_) : c(cfg), lane(lane_) {}
+
+    __device__ __forceinline__ void bind(uint8_t *blk_s, uint64_t *vrow, int e) {
+        hdr_s = reinterpret_cast<EnvHdr *>(blk_s);
+        pos_s = reinterpret_cast<uint16_t *>(blk_s + c.off_pos);
+        tgt_s = reinterpret_cast<uint16_t *>(blk_s + c.off_tgt);
+        ord_s = reinterpret_cast<uint16_t *>(blk_s + c.off_ord);
+        meta_s = blk_s + c.off_meta;
+        vrow_s = vrow;
+        tasks_e = c.tasks + (size_t)e * c.T;
+    }
+
+    // coalesced copy of the scene block global -> shared (uint4 granules)
+    __device__ __forceinline__ void load_block(uint8_t *blk_s, int e) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(c.state + (size_t)e * c.env_stride);
+        uint4 *dst = reinterpret_cast<uint4 *>(blk_s);
+        for (int i = lane; i < c.env_stride / 16; i += 32) dst[i] = src[i];
+        __syncwarp();
+    }
+    __device__ __forceinline__ void store_block(const uint8_t *blk_s, int e) {
+        __syncwarp();
+        uint4 *dst = reinterpret_cast<uint4 *>(c.state + (size_t)e * c.env_stride);
+        const uint4 *src = reinterpret_cast<const uint4 *>(blk_s);
+        for (int i = lane; i < c.env_stride / 16; i += 32) dst[i] = src[i];
+    }
+
+    __device__ __forceinline__ void load_static() {
+#pragma unroll
+        for (int s = 0; s < RPL; s++) {
+            const int r = lane * RPL + s;
+#pragma unroll
+            for (int i = 0; i < NW; i++) {
+                const bool ok = r < c.H;
+                stor[s].w[i] = ok ? __ldg(c.storage_rows + r * NW + i) : 0ull;
+                pick[s].w[i] = ok ? __ldg(c.picking_rows + r * NW + i) : 0ull;
+                inb[s].w[i] = ok ? __ldg(c.inb_rows + r * NW + i) : 0ull;
+            }
+        }
+    }
+
+    __device__ __forceinline__ void hdr_to_regs() {
+        tick = hdr_s->tick; cursor = hdr_s->cursor; n_done = hdr_s->n_done;
+        n_created = hdr_s->n_created; finished = hdr_s->finished; over = hdr_s->over;
+        acted_mask = hdr_s->acted_mask;
+    }
+    __device__ __forceinline__ void regs_to_hdr() {
+        if (lane == 0) {
+            hdr_s->tick = tick; hdr_s->cursor = cursor; hdr_s->n_done = n_done;
+            hdr_s->n_created = (uint16_t)n_created; hdr_s->finished = (uint8_t)finished;
+            hdr_s->over = (uint8_t)over; hdr_s->acted_mask = acted_mask;
+        }
+        __syncwarp();
+    }
+
+    __device__ __forceinline__ void build_occ() {
+#pragma unroll
+        for (int s = 0; s < RPL; s++) occ[s] = rzero<NW>();
+        for (int j = 0; j < n_created; j++) {
+            const int p = pos_s[j];
+            set_bit<NW, RPL>(occ, (p >> 8) - 1, (p & 255) - 1, lane);
+        }
+    }
+
+    __device__ __forceinline__ Agv load_agv(int i) const {
+        Agv a;
+        const int p = pos_s[i], t = tgt_s[i], m = meta_s[i];
+        a.x = p & 255; a.y = p >> 8; a.tx = t & 255; a.ty = t >> 8;
+        a.stage = m & 3; a.loaded = (m >> 2) & 1; a.idle = (m >> 3) & 1; a.order = ord_s[i];
+        return a;
+    }
+    __device__ __forceinline__ void store_agv(int i, const Agv &a) {
+        if (lane == 0) {
+            pos_s[i] = (uint16_t)(a.x | (a.y << 8));
+            tgt_s[i] = (uint16_t)(a.tx | (a.ty << 8));
+            ord_s[i] = (uint16_t)a.order;
+            meta_s[i] = (uint8_t)meta_pack(a);
+        }
+        __syncwarp();
+    }
+
+    // any created AGV j != i standing on cell code (x | y<<8)?   (warp ballot)
+    __device__ __forceinline__ bool other_at(int i, int cell) const {
+        bool m = false;
+        for (int j = lane; j < n_created; j += 32) m |= (j != i) && (pos_s[j] == cell);
+        return __any_sync(FULL, m);
+    }
+
+    // Explorer.load_condition, Explorer.py:102-116
+    __device__ __forceinline__ void load_condition(Agv &a) const {
+        if (c.always_loaded) a.loaded = 1;
+        else if (c.always_empty) a.loaded = 0;
+        else a.loaded = (a.stage == 0) ? 0 : 1;
+    }
+    // Explorer.get_task, Explorer.py:68-100 (AGV is created)
+    __device__ __forceinline__ void get_task(Agv &a) {
+        if ((uint32_t)c.T == cursor && a.stage == 0) {
+            a.idle = 1;
+            if ((uint32_t)c.T == n_done) finished = 1;
+            return;  // target_position / loaded keep their values
+        }
+        if (a.stage == 0) a.order = (int)(cursor++);
+        const uint32_t t = __ldg(tasks_e + a.order);
+        if (a.stage == 1) { a.tx = (t >> 16) & 255; a.ty = (t >> 24) & 255; }
+        else { a.tx = t & 255; a.ty = (t >> 8) & 255; }
+        load_condition(a);
+    }
+    // Explorer.continue_working, Explorer.py:251-259
+    __device__ __forceinline__ void continue_working(Agv &a) {
+        a.stage++;
+        if (a.stage == 3) { a.stage = 0; n_done++; }
+        get_task(a);
+    }
+
+    // Scene.init (Scene.py:61-65) + create_explorer of AGV 0 (Scene.py:86)
+    __device__ __forceinline__ void reset() {
+        tick = 0; cursor = 0; n_done = 0; finished = 0; over = 0; acted_mask = 0;
+        for (int j = lane; j < c.N; j += 32) {
+            pos_s[j] = (uint16_t)(1 | (1 << 8));
+            ord_s[j] = 0; meta_s[j] = 0;  // tgt_s is NOT reset (Explorer.py:45-58)
+        }
+        __syncwarp();
+        n_created = 0;
+        if (c.N > 0) {
+            n_created = 1;
+            Agv a = load_agv(0);
+            get_task(a);
+            store_agv(0, a);
+        }
+    }
+
+    // Scene.py:124-134: 1 act, 0 skip (idle), -1 break (uncreated), -2 return (finished)
+    __device__ __forceinline__ int turn_state(int i) const {
+        if (i >= n_created) return -1;
+        if (finished) return -2;
+        if ((meta_s[i] >> 3) & 1) return 0;
+        return 1;
+    }
+
+    // base passability by cell code and load state (Explorer.py:266-272, StateManager.py:92-120)
+    __device__ __forceinline__ Row<NW> base_row(int s, int loaded) const {
+        Row<NW> b = randn(inb[s], pick[s]);
+        if (loaded) b = randn(b, stor[s]);
+        return b;
+    }
+
+    // matrix (b): StateManager.create_path_matrix, StateManager.py:43-61
+    __device__ __forceinline__ void valid_b(const Agv &a, int i, Row<NW> (&v)[RPL]) const {
+        const bool shared = other_at(i, a.x | (a.y << 8));
+        Row<NW> own[RPL], oth[RPL];
+#pragma unroll
+        for (int s = 0; s < RPL; s++) { own[s] = rzero<NW>(); oth[s] = occ[s]; }
+        set_bit<NW, RPL>(own, a.y - 1, a.x - 1, lane);
+        if (!shared) clear_bit<NW, RPL>(oth, a.y - 1, a.x - 1, lane);
+        set_bit<NW, RPL>(own, a.ty - 1, a.tx - 1, lane);
+#pragma unroll
+        for (int s = 0; s < RPL; s++) v[s] = randn(ror(base_row(s, a.loaded), own[s]), oth[s]);
+    }
+    // matrix (a): Explorer.create_valid_matrix, Explorer.py:261-284
+    __device__ __forceinline__ void valid_a(const Agv &a, Row<NW> (&v)[RPL]) const {
+        Row<NW> tg[RPL], blk[RPL];
+#pragma unroll
+        for (int s = 0; s < RPL; s++) { tg[s] = rzero<NW>(); blk[s] = rzero<NW>(); }
+        set_bit<NW, RPL>(tg, a.ty - 1, a.tx - 1, lane);
+        if (c.N > 1) {
+#pragma unroll
+            for (int s = 0; s < RPL; s++) blk[s] = occ[s];
+            if (n_created < c.N) set_bit<NW, RPL>(blk, 0, 0, lane);  // uncreated AGVs park at (1,1)
+        }
+#pragma unroll
+        for (int s = 0; s < RPL; s++) v[s] = randn(ror(base_row(s, a.loaded), tg[s]), blk[s]);
+    }
+
+    __device__ __forceinline__ void rows_to_smem(const Row<NW> (&v)[RPL]) {
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < RPL; s++) {
+            const int r = lane * RPL + s;
+            if (r < c.H) {
+#pragma unroll
+                for (int i = 0; i < NW; i++) vrow_s[r * NW + i] = v[s].w[i];
+            }
+        }
+        __syncwarp();
+    }
+
+    // StateManager.create_state(obs_clip=True) (StateManager.py:14-41,145-192) into a
+    // [3,K,K] bf16 record in shared memory; vrow_s holds matrix (b).
+    __device__ __forceinline__ void encode_clip(uint16_t *dst, const Agv &a) const {
+        const int P = c.P, K = c.K, KK = K * K, n = 3 * KK;
+        const int cx = a.x - 1, cy = a.y - 1;
+        int tdx = a.tx - a.x, tdy = a.ty - a.y;
+        tdx = max(-P, min(P, tdx)) + P;
+        tdy = max(-P, min(P, tdy)) + P;
+        for (int idx = lane; idx < n; idx += 32) {
+            const int ch = idx / KK, rem = idx - ch * KK, wy = rem / K, wx = rem - wy * K;
+            bool v;
+            if (ch == 0) v = (wy == P) && (wx == P);
+            else if (ch == 1) v = (wy == tdy) && (wx == tdx);
+            else {
+                const int r = cy - P + wy, cc = cx - P + wx;
+                v = false;
+                if (r >= 0 && r < c.H && cc >= 0 && cc < c.W) v = (vrow_s[r * NW + (cc >> 6)] >> (cc & 63)) & 1ull;
+            }
+            dst[idx] = v ? BF16_ONE : (uint16_t)0;
+        }
+    }
+    // StateManager.create_state(obs_clip=False) straight to a [3,H,W] bf16 record in HBM
+    __device__ __forceinline__ void encode_full(uint16_t *dst, const Agv &a) const {
+        const int H = c.H, W = c.W, HW = H * W, n = 3 * HW;
+        const int cpos = (a.y - 1) * W + (a.x - 1), tpos = (a.ty - 1) * W + (a.tx - 1);
+        if ((W & 7) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+            // 8 consecutive columns of one row of one channel per 16-byte store
+            const int nv = n >> 3;
+            for (int v8 = lane; v8 < nv; v8 += 32) {
+                const int flat = v8 << 3;
+                const int ch = flat / HW, p = flat - ch * HW;
+                unsigned bits;
+                if (ch == 0) bits = (cpos >= p && cpos < p + 8) ? (1u << (cpos - p)) : 0u;
+                else if (ch == 1) bits = (tpos >= p && tpos < p + 8) ? (1u << (tpos - p)) : 0u;
+                else {
+                    const int r = p / W, cc = p - r * W;
+                    bits = (unsigned)((vrow_s[r * NW + (cc >> 6)] >> (cc & 63)) & 0xffull);
+                }
+                uint4 o;
+                o.x = ((bits & 1u) ? (unsigned)BF16_ONE : 0u) | ((bits & 2u) ? ((unsigned)BF16_ONE << 16) : 0u);
+                o.y = ((bits & 4u) ? (unsigned)BF16_ONE : 0u) | ((bits & 8u) ? ((unsigned)BF16_ONE << 16) : 0u);
+                o.z = ((bits & 16u) ? (unsigned)BF16_ONE : 0u) | ((bits & 32u) ? ((unsigned)BF16_ONE << 16) : 0u);
+                o.w = ((bits & 64u) ? (unsigned)BF16_ONE : 0u) | ((bits & 128u) ? ((unsigned)BF16_ONE << 16) : 0u);
+                reinterpret_cast<uint4 *>(dst)[v8] = o;
+            }
+        } else {
+            for (int idx = lane; idx < n; idx += 32) {
+                const int ch = idx / HW, p = idx - ch * HW;
+                bool v;
+                if (ch == 0) v = (p == cpos);
+                else if (ch == 1) v = (p == tpos);
+                else {
+                    const int r = p / W, cc = p - r * W;
+                    v = (vrow_s[r * NW + (cc >> 6)] >> (cc & 63)) & 1ull;
+                }
+                dst[idx] = v ? BF16_ONE : (uint16_t)0;
+            }
+        }
+    }
+
+    // Scene.check_new_veh, Scene.py:354-366
+    __device__ __forceinline__ void spawn() {
+        if (n_created >= c.N) return;
+        const bool occupied = test_any(occ, 0, 0);
+        if (occupied) return;
+        const int k = n_created++;
+        Agv a = load_agv(k);
+        get_task(a);
+        store_agv(k, a);
+        set_bit<NW, RPL>(occ, a.y - 1, a.x - 1, lane);
+    }
+    __device__ __forceinline__ bool test_any(const Row<NW> (&rows)[RPL], int r, int cc) const {
+        return __any_sync(FULL, test_bit_local<NW, RPL>(rows, r, cc, lane));
+    }
+};
+
+struct TurnOut {
+    int action;
+    float reward;
+    int done;
+    int plen;
+    int slen;
+};
+
+// One AGV turn = [encode obs] -> action -> Explorer.execute_action (Explorer.py:131-208)
+// -> Scene.py:155 correction -> [encode next_obs].  Warp-uniform control flow.
+// obs_dst / next_dst: destination record (shared staging for OBS_CLIP, global for
+// OBS_FULL) or nullptr.
+template <int NW, int RPL>
+__device__ __forceinline__ void do_turn(WarpScene<NW, RPL> &ws, int i, int proto, int policy, int given,
+                                        int obs_kind, uint16_t *obs_dst, uint16_t *next_dst, TurnOut &out) {
+    const DevCfg &c = ws.c;
+    const int lane = ws.lane;
+    Agv a = ws.load_agv(i);
+    Row<NW> v[RPL];
+    const bool want_obs = (obs_kind != OBS_NONE) && (obs_dst != nullptr);
+    const bool guided = (policy == POLICY_GUIDED) || (policy == POLICY_GIVEN && given < 0);
+    if (want_obs || guided) ws.valid_b(a, i, v);
+    if (want_obs) {
+        ws.rows_to_smem(v);
+        if (obs_kind == OBS_CLIP) ws.encode_clip(obs_dst, a);
+        else ws.encode_full(obs_dst, a);
+    }
+    int action, plen = 0;
+    if (guided) {
+        action = warp_bfs<NW, RPL>(v, a.x - 1, a.y - 1, a.tx - 1, a.ty - 1, c.H, c.W, lane, plen);
+    } else if (policy == POLICY_ASTAR) {
+        ws.valid_a(a, v);
+        action = warp_bfs<NW, RPL>(v, a.x - 1, a.y - 1, a.tx - 1, a.ty - 1, c.H, c.W, lane, plen);
+    } else {
+        action = given;
+        if (action > A_STOP) {  // the reference raises KeyError (utils.py:21); counted, treated as STOP
+            if (lane == 0) atomicAdd(c.counters + 2, 1ull);
+            action = A_STOP;
+        }
+    }
+    // ---- Explorer.check_action, Explorer.py:151-208
+    const int dx = (action == A_RIGHT) - (action == A_LEFT);
+    const int dy = (action == A_DOWN) - (action == A_UP);
+    const int nx = a.x + dx, ny = a.y + dy;
+    int r = 0, end = 0, slen = 0xFFFF;
+    double rshaped = 0.0;
+    bool use_shaped = false;
+    const bool oob = nx < 1 || ny < 1 || nx > c.W || ny > c.H;
+    if (oob) { r = -1; end = 1; }
+    else {
+        const int code = __ldg(c.grid + (ny - 1) * c.W + (nx - 1));
+        const bool at_target = (nx == a.tx) && (ny == a.ty);
+        if (code == 1 && a.loaded && !at_target) { r = -1; end = 1; }
+        else if (code == 2 && !at_target) { r = -1; end = 1; }
+        else if (proto == PROTO_INTELLIGENT && ws.other_at(i, nx | (ny << 8))) { r = -1; end = 1; }
+        else if (at_target) { r = 1; ws.continue_working(a); }
+        else if (c.shaped) {
+            // Explorer.rectify_reward (Explorer.py:210-249): only path_length_new matters
+            ws.valid_a(a, v);
+            int l = 0;
+            warp_bfs<NW, RPL>(v, nx - 1, ny - 1, a.tx - 1, a.ty - 1, c.H, c.W, lane, l);
+            slen = l;
+            const double M = 0.5 * (double)(c.H + c.W);
+            rshaped = 0.001 * (M - (double)l) / M;
+            use_shaped = true;
+        }
+    }
+    // ---- Explorer.py:145-148: the move is applied iff not is_end
+    if (!end && (dx | dy)) {
+        const int oldcell = a.x | (a.y << 8);
+        const bool still = ws.other_at(i, oldcell);
+        if (!still) clear_bit<NW, RPL>(ws.occ, a.y - 1, a.x - 1, lane);
+        a.x = nx; a.y = ny;
+        set_bit<NW, RPL>(ws.occ, ny - 1, nx - 1, lane);
+    }
+    ws.store_agv(i, a);
+    if (proto == PROTO_INTELLIGENT) {
+        if (ws.finished || (long long)ws.tick >= c.max_steps) end = 1;  // Scene.py:155
+        if (end) ws.over = 1;
+    } else {
+        end = 0;  // is_end is ignored by the loop in A_star / manual mode (Scene.py:159-162)
+    }
+    ws.acted_mask |= (1ull << i);
+    if (lane == 0) {
+        atomicAdd(c.counters + 0, 1ull);
+        if (end) atomicAdd(c.counters + 1, 1ull);
+    }
+    if (next_dst != nullptr && obs_kind != OBS_NONE) {
+        // store_info's create_state on the snapshot after the move (Scene.py:156)
+        ws.valid_b(a, i, v);
+        ws.rows_to_smem(v);
+        if (obs_kind == OBS_CLIP) ws.encode_clip(next_dst, a);
+        else ws.encode_full(next_dst, a);
+    }
+    out.action = action;
+    out.reward = use_shaped ? (float)rshaped : (float)r;
+    out.done = end;
+    out.plen = plen;
+    out.slen = slen;
+}
+
+// copy nbytes shared -> global with the widest aligned stores available
+__device__ __forceinline__ void flush_bytes(uint8_t *dst, const uint8_t *src, int nbytes, int lane) {
+    __syncwarp();
+    const uintptr_t d = reinterpret_cast<uintptr_t>(dst), s = reinterpret_cast<uintptr_t>(src);
+    if (((d | s) & 15) == 0 && (nbytes & 15) == 0) {
+        for (int i = lane; i < (nbytes >> 4); i += 32)
+            reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(src)[i];
+    } else if (((d | s) & 3) == 0 && (nbytes & 3) == 0) {
+        for (int i = lane; i < (nbytes >> 2); i += 32)
+            reinterpret_cast<uint32_t *>(dst)[i] = reinterpret_cast<const uint32_t *>(src)[i];
+    } else {
+        for (int i = lane; i < (nbytes >> 1); i += 32)
+            reinterpret_cast<uint16_t *>(dst)[i] = reinterpret_cast<const uint16_t *>(src)[i];
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void zero_global(uint16_t *dst, int n_elems, int lane) {
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (n_elems & 7) == 0) {
+        for (int i = lane; i < (n_elems >> 3); i += 32) reinterpret_cast<uint4 *>(dst)[i] = make_uint4(0, 0, 0, 0);
+    } else {
+        for (int i = lane; i < n_elems; i += 32) dst[i] = 0;
+    }
+}
+
+}  // namespace agv

@@ -1,0 +1,715 @@
+// agv_kernels.cu -- kernels + C ABI (include/agv_b200.h) of the batched scene.
+// sm_100a only.  See agv_core.cuh for the warp-per-scene device core.
+#include "agv_core.cuh"
+#include "../../include/agv_b200.h"
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace agv {
+
+static std::atomic<uint64_t> g_launches{0};
+static int g_last_cuda = 0;
+
+struct TickArgs {
+    int proto, policy, obs_kind;
+    const int8_t *action;
+    int8_t *act_out;
+    float *reward;
+    uint8_t *done;
+    uint16_t *plen, *slen;
+    uint16_t *obs, *next_obs;
+    int rec_elems;  // bf16 elements per obs record
+    int group;      // records per 16-byte aligned flush group (OBS_CLIP)
+    // per-warp shared memory plan (bytes)
+    int per_warp, off_blk, off_vrow, off_act, off_done, off_plen, off_slen, off_rew, off_stage, off_stage2;
+};
+
+struct StepArgs {
+    int k, proto, obs_kind, post, matrix;
+    const int8_t *action;
+    int8_t *action_out;
+    float *reward;
+    uint8_t *done, *acted;
+    uint16_t *slen, *plen;
+    uint16_t *obs;
+    int rec_elems;
+    int per_warp, off_blk, off_vrow, off_stage;
+};
+
+#define WARP_PROLOGUE(ARGS)                                                        \
+    extern __shared__ __align__(16) uint8_t smem[];                                \
+    const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;                     \
+    const int e = blockIdx.x * (blockDim.x >> 5) + wic;                            \
+    if (e >= c.E) return;                                                          \
+    uint8_t *wbase = smem + (size_t)wic * ARGS.per_warp;                           \
+    WarpScene<NW, RPL> ws(c, lane);                                                \
+    ws.bind(wbase + ARGS.off_blk, reinterpret_cast<uint64_t *>(wbase + ARGS.off_vrow), e); \
+    ws.load_block(wbase + ARGS.off_blk, e);                                        \
+    ws.load_static();                                                              \
+    ws.hdr_to_regs();
+
+// ---------------------------------------------------------------- fused tick
+template <int NW, int RPL>
+__global__ void __launch_bounds__(128) k_tick(const DevCfg c, const TickArgs t) {
+    WARP_PROLOGUE(t)
+    int8_t *o_act = reinterpret_cast<int8_t *>(wbase + t.off_act);
+    uint8_t *o_done = wbase + t.off_done;
+    uint16_t *o_plen = reinterpret_cast<uint16_t *>(wbase + t.off_plen);
+    uint16_t *o_slen = reinterpret_cast<uint16_t *>(wbase + t.off_slen);
+    float *o_rew = reinterpret_cast<float *>(wbase + t.off_rew);
+    uint16_t *stage = reinterpret_cast<uint16_t *>(wbase + t.off_stage);
+    uint16_t *stage2 = reinterpret_cast<uint16_t *>(wbase + t.off_stage2);
+    const int N = c.N, R = t.rec_elems, G = t.group;
+    const bool clip = t.obs_kind == OBS_CLIP, full = t.obs_kind == OBS_FULL;
+
+    bool live = true;
+    if (ws.over) {
+        if (c.auto_reset) ws.reset();
+        else live = false;
+    }
+    if (live) { ws.build_occ(); ws.tick++; ws.acted_mask = 0; }
+    bool stopped = !live;
+    for (int i = 0; i < N; i++) {
+        bool act = false;
+        if (!stopped && !ws.over) {
+            const int st = ws.turn_state(i);
+            if (st == -1) stopped = true;                    // Scene.py:127-128 break
+            else if (st == -2) {                             // Scene.py:129-130 return
+                ws.over = 1;
+                if (lane == 0) atomicAdd(c.counters + 1, 1ull);
+            } else if (st == 1) act = true;
+        }
+        const size_t rec = (size_t)e * N + i;
+        uint16_t *od = nullptr, *nd = nullptr;
+        if (clip) {
+            if (t.obs) od = stage + (size_t)(i % G) * R;
+            if (t.next_obs) nd = stage2 + (size_t)(i % G) * R;
+        } else if (full) {
+            if (t.obs) od = t.obs + rec * R;
+            if (t.next_obs) nd = t.next_obs + rec * R;
+        }
+        if (act) {
+            TurnOut o;
+            const int given = (t.policy == POLICY_GIVEN && t.action) ? (int)t.action[rec] : -1;
+            do_turn<NW, RPL>(ws, i, t.proto, t.policy, given, t.obs_kind, od, nd, o);
+            if (lane == 0) {
+                o_act[i] = (int8_t)o.action; o_done[i] = (uint8_t)o.done; o_rew[i] = o.reward;
+                o_plen[i] = (uint16_t)o.plen; o_slen[i] = (uint16_t)o.slen;
+            }
+        } else {
+            if (lane == 0) { o_act[i] = -1; o_done[i] = 0; o_rew[i] = 0.f; o_plen[i] = 0; o_slen[i] = 0xFFFF; }
+            if (clip) {
+                if (od) for (int q = lane; q < R; q += 32) od[q] = 0;
+                if (nd) for (int q = lane; q < R; q += 32) nd[q] = 0;
+            } else if (full) {
+                if (od) zero_global(od, R, lane);
+                if (nd) zero_global(nd, R, lane);
+            }
+        }
+        if (clip && (((i + 1) % G) == 0 || i == N - 1)) {
+            const int g0 = i - (i % G), nrec = i - g0 + 1;
+            const size_t off = ((size_t)e * N + g0) * R;
+            if (t.obs) flush_bytes(reinterpret_cast<uint8_t *>(t.obs + off), reinterpret_cast<uint8_t *>(stage),
+                                   nrec * R * 2, lane);
+            if (t.next_obs) flush_bytes(reinterpret_cast<uint8_t *>(t.next_obs + off),
+                                        reinterpret_cast<uint8_t *>(stage2), nrec * R * 2, lane);
+        }
+    }
+    if (live && !ws.over) ws.spawn();
+    ws.regs_to_hdr();
+    ws.store_block(wbase + t.off_blk, e);
+    for (int j = lane; j < N; j += 32) {
+        const size_t rec = (size_t)e * N + j;
+        if (t.act_out) t.act_out[rec] = o_act[j];
+        if (t.done) t.done[rec] = o_done[j];
+        if (t.reward) t.reward[rec] = o_rew[j];
+        if (t.plen) t.plen[rec] = o_plen[j];
+        if (t.slen) t.slen[rec] = o_slen[j];
+    }
+}
+
+// ---------------------------------------------------------------- sub-step kernels
+template <int NW, int RPL>
+__global__ void __launch_bounds__(128) k_reset(const DevCfg c, const StepArgs t, const uint8_t *mask) {
+    WARP_PROLOGUE(t)
+    if (mask && !mask[e]) return;
+    ws.reset();
+    ws.regs_to_hdr();
+    ws.store_block(wbase + t.off_blk, e);
+}
+
+template <int NW, int RPL>
+__global__ void __launch_bounds__(128) k_begin_tick(const DevCfg c, const StepArgs t) {
+    WARP_PROLOGUE(t)
+    if (ws.over && c.auto_reset) ws.reset();
+    if (!ws.over) { ws.tick++; ws.acted_mask = 0; }
+    ws.regs_to_hdr();
+    ws.store_block(wbase + t.off_blk, e);
+}
+
+template <int NW, int RPL>
+__global__ void __launch_bounds__(128) k_end_tick(const DevCfg c, const StepArgs t) {
+    WARP_PROLOGUE(t)
+    if (ws.over) return;
+    ws.build_occ();
+    ws.spawn();
+    ws.regs_to_hdr();
+    ws.store_block(wbase + t.off_blk, e);
+}
+
+template <int NW, int RPL>
+__global__ void __launch_bounds__(128) k_encode(const DevCfg c, const StepArgs t) {
+    WARP_PROLOGUE(t)
+    const int k = t.k, R = t.rec_elems;
+    bool go;
+    if (t.post) go = (ws.acted_mask >> k) & 1ull;
+    else go = (!ws.over) && ws.turn_state(k) == 1;
+    if (t.acted && lane == 0) t.acted[e] = go ? 1 : 0;
+    if (!t.obs) return;
+    uint16_t *dst = t.obs + (size_t)e * R;
+    if (!go) { zero_global(dst, R, lane); return; }
+    ws.build_occ();
+    Agv a = ws.load_agv(k);
+    Row<NW> v[RPL];
+    ws.valid_b(a, k, v);
+    ws.rows_to_smem(v);
+    if (t.obs_kind == OBS_CLIP) {
+        uint16_t *stage = reinterpret_cast<uint16_t *>(wbase + t.off_stage);
+        ws.encode_clip(stage, a);
+        flush_bytes(reinterpret_cast<uint8_t *>(dst), reinterpret_cast<uint8_t *>(stage), R * 2, lane);
+    } else {
+        ws.encode_full(dst, a);
+    }
+}
+
+template <int NW, int RPL>
+__global__ void __launch_bounds__(128) k_bfs_action(const DevCfg c, const StepArgs t) {
+    WARP_PROLOGUE(t)
+    const int k = t.k;
+    const bool go = (!ws.over) && ws.turn_state(k) == 1;
+    int action = -1, plen = 0;
+    if (go) {
+        ws.build_occ();
+        Agv a = ws.load_agv(k);
+        Row<NW> v[RPL];
+        if (t.matrix == 0) ws.valid_a(a, v);
+        else ws.valid_b(a, k, v);
+        action = warp_bfs<NW, RPL>(v, a.x - 1, a.y - 1, a.tx - 1, a.ty - 1, c.H, c.W, lane, plen);
+    }
+    if (lane == 0) {
+        if (t.action_out) t.action_out[e] = (int8_t)action;
+        if (t.plen) t.plen[e] = (uint16_t)plen;
+    }
+}
+
+template <int NW, int RPL>
+__global__ void __launch_bounds__(128) k_step_turn(const DevCfg c, const StepArgs t) {
+    WARP_PROLOGUE(t)
+    const int k = t.k;
+    TurnOut o;
+    o.action = -1; o.reward = 0.f; o.done = 0; o.plen = 0; o.slen = 0xFFFF;
+    bool acted = false;
+    if (!ws.over) {
+        const int st = ws.turn_state(k);
+        if (st == -2) {
+            ws.over = 1;
+            if (lane == 0) atomicAdd(c.counters + 1, 1ull);
+        } else if (st == 1) {
+            ws.build_occ();
+            const int given = t.action ? (int)t.action[e] : -1;
+            do_turn<NW, RPL>(ws, k, t.proto, POLICY_GIVEN, given, OBS_NONE, nullptr, nullptr, o);
+            acted = true;
+        }
+        ws.regs_to_hdr();
+        ws.store_block(wbase + t.off_blk, e);
+    }
+    if (lane == 0) {
+        if (t.reward) t.reward[e] = o.reward;
+        if (t.done) t.done[e] = (uint8_t)o.done;
+        if (t.acted) t.acted[e] = acted ? 1 : 0;
+        if (t.slen) t.slen[e] = (uint16_t)o.slen;
+        if (t.action_out) t.action_out[e] = (int8_t)o.action;
+    }
+}
+
+// ---------------------------------------------------------------- standalone BFS
+template <int NW, int RPL>
+__device__ __forceinline__ void rows_from_bytes(const uint8_t *m, int H, int W, int lane, Row<NW> (&v)[RPL]) {
+#pragma unroll
+    for (int s = 0; s < RPL; s++) {
+        v[s] = rzero<NW>();
+        const int r = lane * RPL + s;
+        if (r < H) {
+            for (int cc = 0; cc < W; cc++)
+                if (m[r * W + cc] == 1) {
+#pragma unroll
+                    for (int i = 0; i < NW; i++)
+                        if (i == (cc >> 6)) v[s].w[i] |= 1ull << (cc & 63);
+                }
+        }
+    }
+}
+
+template <int NW, int RPL>
+__global__ void __launch_bounds__(128) k_bfs_batch(int B, int H, int W, const uint8_t *valid, const int32_t *start,
+                                                   const int32_t *target, int8_t *action, int32_t *pathlen,
+                                                   uint8_t *found) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= B) return;
+    Row<NW> v[RPL];
+    rows_from_bytes<NW, RPL>(valid + (size_t)b * H * W, H, W, lane, v);
+    const int sx = start[2 * b], sy = start[2 * b + 1], tx = target[2 * b], ty = target[2 * b + 1];
+    int len = 0;
+    const int a = warp_bfs<NW, RPL>(v, sx, sy, tx, ty, H, W, lane, len);
+    if (lane == 0) {
+        if (action) action[b] = (int8_t)a;
+        if (pathlen) pathlen[b] = len;
+        if (found) found[b] = (uint8_t)((sx == tx && sy == ty) || len > 0);
+    }
+}
+
+template <int NW, int RPL>
+__global__ void __launch_bounds__(128) k_bfs_field(int B, int H, int W, const uint8_t *valid, const int32_t *target,
+                                                   uint16_t *dist) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= B) return;
+    Row<NW> v[RPL];
+    rows_from_bytes<NW, RPL>(valid + (size_t)b * H * W, H, W, lane, v);
+    warp_bfs_field<NW, RPL>(v, target[2 * b], target[2 * b + 1], H, W, lane, dist + (size_t)b * H * W);
+}
+
+__global__ void k_init_state(const DevCfg c) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= c.E) return;
+    uint8_t *blk = c.state + (size_t)e * c.env_stride;
+    for (int i = 0; i < c.env_stride; i++) blk[i] = 0;
+    EnvHdr *h = reinterpret_cast<EnvHdr *>(blk);
+    h->over = 1;
+    uint16_t *pos = reinterpret_cast<uint16_t *>(blk + c.off_pos);
+    uint16_t *tgt = reinterpret_cast<uint16_t *>(blk + c.off_tgt);
+    for (int j = 0; j < c.N; j++) { pos[j] = 0x0101; tgt[j] = 0x0101; }  // Explorer.py:27-28
+}
+
+}  // namespace agv
+
+// =================================================================== host side
+using namespace agv;
+
+struct AgvHandle {
+    AgvConfig cfg;
+    DevCfg dc;
+    int NW, RPL;
+    uint8_t *d_state = nullptr;
+    uint32_t *d_tasks = nullptr;
+    uint8_t *d_grid = nullptr;
+    uint64_t *d_rows = nullptr;  // storage | picking | inb
+    unsigned long long *d_counters = nullptr;
+    // staging for agv_tick_host
+    int8_t *d_action = nullptr, *d_act_out = nullptr;
+    float *d_reward = nullptr;
+    uint8_t *d_done = nullptr;
+    std::vector<uint8_t> h_state;
+};
+
+static inline int align16(int x) { return (x + 15) & ~15; }
+
+#define CUDA_TRY(expr)                              \
+    do {                                            \
+        cudaError_t _e = (expr);                    \
+        if (_e != cudaSuccess) {                    \
+            g_last_cuda = (int)_e;                  \
+            return AGV_E_CUDA;                      \
+        }                                           \
+    } while (0)
+
+#define DISPATCH(h, CALL)                                                  \
+    do {                                                                   \
+        if (h->NW == 1 && h->RPL == 1) { CALL(1, 1); }                     \
+        else if (h->NW == 1 && h->RPL == 2) { CALL(1, 2); }                \
+        else if (h->NW == 1 && h->RPL == 4) { CALL(1, 4); }                \
+        else if (h->NW == 2 && h->RPL == 1) { CALL(2, 1); }                \
+        else if (h->NW == 2 && h->RPL == 2) { CALL(2, 2); }                \
+        else { CALL(2, 4); }                                               \
+    } while (0)
+
+static int pick_variant(int H, int W, int *NW, int *RPL) {
+    if (H < 1 || W < 1 || H > 128 || W > 128) return AGV_E_UNSUPPORTED;
+    *NW = W <= 64 ? 1 : 2;
+    *RPL = H <= 32 ? 1 : (H <= 64 ? 2 : 4);
+    return AGV_OK;
+}
+
+static int gcd_i(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
+
+static const int WARPS_PER_CTA = 4;
+
+template <typename K, typename... Args>
+static int launch_warps(K kernel, int n_warps, size_t smem_per_warp, cudaStream_t st, Args... args) {
+    const int ctas = (n_warps + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    const size_t smem = smem_per_warp * WARPS_PER_CTA;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { g_last_cuda = (int)e; return AGV_E_CUDA; }
+    }
+    kernel<<<ctas, WARPS_PER_CTA * 32, smem, st>>>(args...);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { g_last_cuda = (int)e; return AGV_E_CUDA; }
+    return AGV_OK;
+}
+
+static void plan_step(const AgvHandle *h, StepArgs &s, int rec_elems) {
+    int off = 0;
+    s.off_blk = off; off += align16(h->dc.env_stride);
+    s.off_vrow = off; off += align16(h->cfg.H * h->NW * 8);
+    s.off_stage = off; off += align16(rec_elems * 2);
+    s.per_warp = off;
+    s.rec_elems = rec_elems;
+}
+
+static int obs_elems(const AgvHandle *h, int obs_kind) {
+    if (obs_kind == AGV_OBS_CLIP) return 3 * h->dc.K * h->dc.K;
+    if (obs_kind == AGV_OBS_FULL) return 3 * h->cfg.H * h->cfg.W;
+    return 0;
+}
+
+extern "C" {
+
+int agv_create(const AgvConfig *cfg, const uint8_t *grid_host, AgvHandle **out) {
+    if (!cfg || !grid_host || !out) return AGV_E_INVALID;
+    if (cfg->E < 1 || cfg->N < 1 || cfg->N > 64 || cfg->T < 0 || cfg->T > 65535 || cfg->P < 0 || cfg->P > 15)
+        return AGV_E_INVALID;
+    int NW, RPL;
+    int rc = pick_variant(cfg->H, cfg->W, &NW, &RPL);
+    if (rc != AGV_OK) return rc;
+    for (int i = 0; i < cfg->H * cfg->W; i++)
+        if (grid_host[i] > 2) return AGV_E_BADGRID;
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    AgvHandle *h = new (std::nothrow) AgvHandle();
+    if (!h) return AGV_E_NOMEM;
+    h->cfg = *cfg; h->NW = NW; h->RPL = RPL;
+    DevCfg &d = h->dc;
+    memset(&d, 0, sizeof(d));
+    d.H = cfg->H; d.W = cfg->W; d.E = cfg->E; d.N = cfg->N; d.T = cfg->T; d.P = cfg->P; d.K = 2 * cfg->P + 1;
+    d.always_loaded = cfg->always_loaded; d.always_empty = cfg->always_empty; d.shaped = cfg->shaped_reward;
+    d.auto_reset = cfg->auto_reset; d.max_steps = cfg->max_steps;
+    const int N = cfg->N;
+    d.off_pos = HDR_BYTES; d.off_tgt = d.off_pos + 2 * N; d.off_ord = d.off_tgt + 2 * N; d.off_meta = d.off_ord + 2 * N;
+    d.env_stride = align16(d.off_meta + N);
+    const size_t HW = (size_t)cfg->H * cfg->W;
+    std::vector<uint64_t> rows(3 * (size_t)cfg->H * NW, 0ull);
+    for (int r = 0; r < cfg->H; r++)
+        for (int cc = 0; cc < cfg->W; cc++) {
+            const int code = grid_host[r * cfg->W + cc];
+            const uint64_t bit = 1ull << (cc & 63);
+            const size_t idx = (size_t)r * NW + (cc >> 6);
+            if (code == 1) rows[idx] |= bit;
+            if (code == 2) rows[(size_t)cfg->H * NW + idx] |= bit;
+            rows[2 * (size_t)cfg->H * NW + idx] |= bit;
+        }
+#define CREATE_TRY(expr)                                                   \
+    do {                                                                   \
+        cudaError_t _e = (expr);                                           \
+        if (_e != cudaSuccess) { g_last_cuda = (int)_e; agv_destroy(h); return AGV_E_CUDA; } \
+    } while (0)
+    CREATE_TRY(cudaMalloc(&h->d_state, (size_t)cfg->E * d.env_stride));
+    CREATE_TRY(cudaMalloc(&h->d_tasks, sizeof(uint32_t) * (size_t)cfg->E * (cfg->T > 0 ? cfg->T : 1)));
+    CREATE_TRY(cudaMemset(h->d_tasks, 0, sizeof(uint32_t) * (size_t)cfg->E * (cfg->T > 0 ? cfg->T : 1)));
+    CREATE_TRY(cudaMalloc(&h->d_grid, HW));
+    CREATE_TRY(cudaMalloc(&h->d_rows, rows.size() * 8));
+    CREATE_TRY(cudaMalloc(&h->d_counters, 3 * sizeof(unsigned long long)));
+    CREATE_TRY(cudaMemset(h->d_counters, 0, 3 * sizeof(unsigned long long)));
+    CREATE_TRY(cudaMemcpy(h->d_grid, grid_host, HW, cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMemcpy(h->d_rows, rows.data(), rows.size() * 8, cudaMemcpyHostToDevice));
+    d.state = h->d_state; d.tasks = h->d_tasks; d.grid = h->d_grid;
+    d.storage_rows = h->d_rows; d.picking_rows = h->d_rows + (size_t)cfg->H * NW;
+    d.inb_rows = h->d_rows + 2 * (size_t)cfg->H * NW;
+    d.counters = h->d_counters;
+    k_init_state<<<(cfg->E + 127) / 128, 128>>>(d);
+    g_launches.fetch_add(1);
+    CREATE_TRY(cudaGetLastError());
+    CREATE_TRY(cudaDeviceSynchronize());
+    *out = h;
+    return AGV_OK;
+}
+
+int agv_destroy(AgvHandle *h) {
+    if (!h) return AGV_OK;
+    cudaSetDevice(h->cfg.device);
+    cudaFree(h->d_state); cudaFree(h->d_tasks); cudaFree(h->d_grid); cudaFree(h->d_rows); cudaFree(h->d_counters);
+    cudaFree(h->d_action); cudaFree(h->d_act_out); cudaFree(h->d_reward); cudaFree(h->d_done);
+    delete h;
+    return AGV_OK;
+}
+
+int agv_set_tasks(AgvHandle *h, const uint8_t *tasks_host, int32_t env_begin, int32_t env_count, void *stream) {
+    if (!h || !tasks_host || env_begin < 0 || env_count < 0 || env_begin + env_count > h->cfg.E) return AGV_E_INVALID;
+    if (h->cfg.T == 0 || env_count == 0) return AGV_OK;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const size_t n = (size_t)env_count * h->cfg.T;
+    for (size_t i = 0; i < n; i++) {
+        const uint8_t *t = tasks_host + 4 * i;
+        if (t[0] < 1 || t[0] > h->cfg.W || t[2] < 1 || t[2] > h->cfg.W || t[1] < 1 || t[1] > h->cfg.H || t[3] < 1 ||
+            t[3] > h->cfg.H)
+            return AGV_E_INVALID;
+    }
+    // [.,4] uint8 (sx,sy,px,py) is bit-identical to the packed little-endian uint32
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemcpyAsync(h->d_tasks + (size_t)env_begin * h->cfg.T, tasks_host, n * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return AGV_OK;
+}
+
+int agv_reset(AgvHandle *h, const uint8_t *env_mask_dev, void *stream) {
+    if (!h) return AGV_E_INVALID;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    StepArgs s; memset(&s, 0, sizeof(s));
+    plan_step(h, s, 0);
+#define CALL(NW_, RPL_) return launch_warps(k_reset<NW_, RPL_>, h->cfg.E, s.per_warp, (cudaStream_t)stream, h->dc, s, env_mask_dev)
+    DISPATCH(h, CALL);
+#undef CALL
+}
+
+int agv_tick(AgvHandle *h, int32_t proto, int32_t policy, int32_t obs_kind, const int8_t *action_dev,
+             int8_t *act_out_dev, float *reward_dev, uint8_t *done_dev, uint16_t *plen_dev, uint16_t *slen_dev,
+             void *obs_dev, void *next_obs_dev, void *stream) {
+    if (!h || proto < 0 || proto > 1 || policy < 0 || policy > 2 || obs_kind < 0 || obs_kind > 2) return AGV_E_INVALID;
+    if (obs_kind == AGV_OBS_NONE && (obs_dev || next_obs_dev)) return AGV_E_INVALID;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    TickArgs t; memset(&t, 0, sizeof(t));
+    t.proto = proto; t.policy = policy; t.obs_kind = (obs_dev || next_obs_dev) ? obs_kind : AGV_OBS_NONE;
+    t.action = action_dev; t.act_out = act_out_dev; t.reward = reward_dev; t.done = done_dev;
+    t.plen = plen_dev; t.slen = slen_dev;
+    t.obs = (uint16_t *)obs_dev; t.next_obs = (uint16_t *)next_obs_dev;
+    const int N = h->cfg.N;
+    t.rec_elems = obs_elems(h, t.obs_kind);
+    t.group = 1;
+    if (t.obs_kind == AGV_OBS_CLIP) {
+        const int rb = t.rec_elems * 2;
+        int g = 16 / gcd_i(rb, 16);
+        // vector flush needs every group start 16-byte aligned: N % g == 0
+        t.group = (N % g == 0) ? g : 1;
+    }
+    int off = 0;
+    t.off_blk = off; off += align16(h->dc.env_stride);
+    t.off_vrow = off; off += align16(h->cfg.H * h->NW * 8);
+    t.off_act = off; off += align16(N);
+    t.off_done = off; off += align16(N);
+    t.off_plen = off; off += align16(2 * N);
+    t.off_slen = off; off += align16(2 * N);
+    t.off_rew = off; off += align16(4 * N);
+    const int stage_bytes = (t.obs_kind == AGV_OBS_CLIP) ? align16(t.group * t.rec_elems * 2) : 0;
+    t.off_stage = off; off += stage_bytes;
+    t.off_stage2 = off; off += stage_bytes;
+    t.per_warp = off;
+#define CALL(NW_, RPL_) return launch_warps(k_tick<NW_, RPL_>, h->cfg.E, t.per_warp, (cudaStream_t)stream, h->dc, t)
+    DISPATCH(h, CALL);
+#undef CALL
+}
+
+int agv_tick_host(AgvHandle *h, int32_t proto, int32_t policy, int32_t obs_kind, const int8_t *action_host,
+                  int8_t *act_out_host, float *reward_host, uint8_t *done_host, void *obs_dev, void *next_obs_dev,
+                  void *stream) {
+    if (!h) return AGV_E_INVALID;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const size_t n = (size_t)h->cfg.E * h->cfg.N;
+    if (!h->d_action) {
+        CUDA_TRY(cudaMalloc(&h->d_action, n));
+        CUDA_TRY(cudaMalloc(&h->d_act_out, n));
+        CUDA_TRY(cudaMalloc(&h->d_reward, n * sizeof(float)));
+        CUDA_TRY(cudaMalloc(&h->d_done, n));
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (policy == AGV_POLICY_GIVEN) {
+        if (!action_host) return AGV_E_INVALID;
+        CUDA_TRY(cudaMemcpyAsync(h->d_action, action_host, n, cudaMemcpyHostToDevice, st));
+    }
+    int rc = agv_tick(h, proto, policy, obs_kind, policy == AGV_POLICY_GIVEN ? h->d_action : nullptr, h->d_act_out,
+                      h->d_reward, h->d_done, nullptr, nullptr, obs_dev, next_obs_dev, stream);
+    if (rc != AGV_OK) return rc;
+    if (act_out_host) CUDA_TRY(cudaMemcpyAsync(act_out_host, h->d_act_out, n, cudaMemcpyDeviceToHost, st));
+    if (reward_host) CUDA_TRY(cudaMemcpyAsync(reward_host, h->d_reward, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (done_host) CUDA_TRY(cudaMemcpyAsync(done_host, h->d_done, n, cudaMemcpyDeviceToHost, st));
+    return AGV_OK;
+}
+
+int agv_begin_tick(AgvHandle *h, void *stream) {
+    if (!h) return AGV_E_INVALID;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    StepArgs s; memset(&s, 0, sizeof(s));
+    plan_step(h, s, 0);
+#define CALL(NW_, RPL_) return launch_warps(k_begin_tick<NW_, RPL_>, h->cfg.E, s.per_warp, (cudaStream_t)stream, h->dc, s)
+    DISPATCH(h, CALL);
+#undef CALL
+}
+
+int agv_end_tick(AgvHandle *h, void *stream) {
+    if (!h) return AGV_E_INVALID;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    StepArgs s; memset(&s, 0, sizeof(s));
+    plan_step(h, s, 0);
+#define CALL(NW_, RPL_) return launch_warps(k_end_tick<NW_, RPL_>, h->cfg.E, s.per_warp, (cudaStream_t)stream, h->dc, s)
+    DISPATCH(h, CALL);
+#undef CALL
+}
+
+int agv_encode(AgvHandle *h, int32_t k, int32_t obs_kind, int32_t post, void *out_dev, uint8_t *will_act_dev,
+               void *stream) {
+    if (!h || k < 0 || k >= h->cfg.N || obs_kind < 1 || obs_kind > 2) return AGV_E_INVALID;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    StepArgs s; memset(&s, 0, sizeof(s));
+    plan_step(h, s, obs_elems(h, obs_kind));
+    s.k = k; s.obs_kind = obs_kind; s.post = post; s.obs = (uint16_t *)out_dev; s.acted = will_act_dev;
+#define CALL(NW_, RPL_) return launch_warps(k_encode<NW_, RPL_>, h->cfg.E, s.per_warp, (cudaStream_t)stream, h->dc, s)
+    DISPATCH(h, CALL);
+#undef CALL
+}
+
+int agv_bfs_action(AgvHandle *h, int32_t k, int32_t matrix, int8_t *action_dev, uint16_t *pathlen_dev, void *stream) {
+    if (!h || k < 0 || k >= h->cfg.N || matrix < 0 || matrix > 1) return AGV_E_INVALID;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    StepArgs s; memset(&s, 0, sizeof(s));
+    plan_step(h, s, 0);
+    s.k = k; s.matrix = matrix; s.action_out = action_dev; s.plen = pathlen_dev;
+#define CALL(NW_, RPL_) return launch_warps(k_bfs_action<NW_, RPL_>, h->cfg.E, s.per_warp, (cudaStream_t)stream, h->dc, s)
+    DISPATCH(h, CALL);
+#undef CALL
+}
+
+int agv_step_turn(AgvHandle *h, int32_t k, int32_t proto, const int8_t *action_dev, float *reward_dev,
+                  uint8_t *done_dev, uint8_t *acted_dev, uint16_t *slen_dev, void *stream) {
+    if (!h || k < 0 || k >= h->cfg.N || proto < 0 || proto > 1) return AGV_E_INVALID;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    StepArgs s; memset(&s, 0, sizeof(s));
+    plan_step(h, s, 0);
+    s.k = k; s.proto = proto; s.action = action_dev; s.reward = reward_dev; s.done = done_dev; s.acted = acted_dev;
+    s.slen = slen_dev;
+#define CALL(NW_, RPL_) return launch_warps(k_step_turn<NW_, RPL_>, h->cfg.E, s.per_warp, (cudaStream_t)stream, h->dc, s)
+    DISPATCH(h, CALL);
+#undef CALL
+}
+
+int agv_get_state(AgvHandle *h, int64_t *hdr_host, int32_t *agv_host, void *stream) {
+    if (!h) return AGV_E_INVALID;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const DevCfg &d = h->dc;
+    h->h_state.resize((size_t)d.E * d.env_stride);
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemcpyAsync(h->h_state.data(), h->d_state, h->h_state.size(), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int e = 0; e < d.E; e++) {
+        const uint8_t *blk = h->h_state.data() + (size_t)e * d.env_stride;
+        EnvHdr hd; memcpy(&hd, blk, sizeof(hd));
+        if (hdr_host) {
+            int64_t *o = hdr_host + 6 * (size_t)e;
+            o[0] = hd.tick; o[1] = hd.cursor; o[2] = hd.n_done; o[3] = hd.finished; o[4] = hd.n_created; o[5] = hd.over;
+        }
+        if (agv_host) {
+            const uint16_t *pos = (const uint16_t *)(blk + d.off_pos), *tgt = (const uint16_t *)(blk + d.off_tgt),
+                           *ord = (const uint16_t *)(blk + d.off_ord);
+            const uint8_t *meta = blk + d.off_meta;
+            for (int j = 0; j < d.N; j++) {
+                int32_t *o = agv_host + 8 * ((size_t)e * d.N + j);
+                o[0] = pos[j] & 255; o[1] = pos[j] >> 8; o[2] = tgt[j] & 255; o[3] = tgt[j] >> 8;
+                o[4] = meta[j] & 3; o[5] = (meta[j] >> 2) & 1; o[6] = (meta[j] >> 3) & 1; o[7] = ord[j];
+            }
+        }
+    }
+    return AGV_OK;
+}
+
+int agv_set_state(AgvHandle *h, const int64_t *hdr_host, const int32_t *agv_host, void *stream) {
+    if (!h || !hdr_host || !agv_host) return AGV_E_INVALID;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const DevCfg &d = h->dc;
+    h->h_state.assign((size_t)d.E * d.env_stride, 0);
+    for (int e = 0; e < d.E; e++) {
+        uint8_t *blk = h->h_state.data() + (size_t)e * d.env_stride;
+        const int64_t *i6 = hdr_host + 6 * (size_t)e;
+        EnvHdr hd; memset(&hd, 0, sizeof(hd));
+        hd.tick = (uint32_t)i6[0]; hd.cursor = (uint32_t)i6[1]; hd.n_done = (uint32_t)i6[2];
+        hd.finished = (uint8_t)i6[3]; hd.n_created = (uint16_t)i6[4]; hd.over = (uint8_t)i6[5];
+        memcpy(blk, &hd, sizeof(hd));
+        uint16_t *pos = (uint16_t *)(blk + d.off_pos), *tgt = (uint16_t *)(blk + d.off_tgt),
+                 *ord = (uint16_t *)(blk + d.off_ord);
+        uint8_t *meta = blk + d.off_meta;
+        for (int j = 0; j < d.N; j++) {
+            const int32_t *a = agv_host + 8 * ((size_t)e * d.N + j);
+            if (a[0] < 1 || a[0] > d.W || a[1] < 1 || a[1] > d.H || a[2] < 1 || a[2] > d.W || a[3] < 1 || a[3] > d.H)
+                return AGV_E_INVALID;
+            pos[j] = (uint16_t)(a[0] | (a[1] << 8)); tgt[j] = (uint16_t)(a[2] | (a[3] << 8));
+            meta[j] = (uint8_t)((a[4] & 3) | (a[5] ? 4 : 0) | (a[6] ? 8 : 0)); ord[j] = (uint16_t)a[7];
+        }
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemcpyAsync(h->d_state, h->h_state.data(), h->h_state.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return AGV_OK;
+}
+
+int agv_read_counters(AgvHandle *h, uint64_t out[3], void *stream) {
+    if (!h || !out) return AGV_E_INVALID;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long tmp[3];
+    CUDA_TRY(cudaMemcpyAsync(tmp, h->d_counters, sizeof(tmp), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemsetAsync(h->d_counters, 0, sizeof(tmp), st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    out[0] = tmp[0]; out[1] = tmp[1]; out[2] = tmp[2];
+    return AGV_OK;
+}
+
+int agv_bfs_batch(int32_t B, int32_t H, int32_t W, const uint8_t *valid_dev, const int32_t *start_dev,
+                  const int32_t *target_dev, int8_t *action_dev, int32_t *pathlen_dev, uint8_t *found_dev,
+                  void *stream) {
+    if (B < 0 || !valid_dev || !start_dev || !target_dev) return AGV_E_INVALID;
+    if (B == 0) return AGV_OK;
+    AgvHandle tmp; AgvHandle *h = &tmp;
+    int rc = pick_variant(H, W, &h->NW, &h->RPL);
+    if (rc != AGV_OK) return rc;
+#define CALL(NW_, RPL_) return launch_warps(k_bfs_batch<NW_, RPL_>, B, 0, (cudaStream_t)stream, B, H, W, valid_dev, start_dev, target_dev, action_dev, pathlen_dev, found_dev)
+    DISPATCH(h, CALL);
+#undef CALL
+}
+
+int agv_bfs_field(int32_t B, int32_t H, int32_t W, const uint8_t *valid_dev, const int32_t *target_dev,
+                  uint16_t *dist_dev, void *stream) {
+    if (B < 0 || !valid_dev || !target_dev || !dist_dev) return AGV_E_INVALID;
+    if (B == 0) return AGV_OK;
+    AgvHandle tmp; AgvHandle *h = &tmp;
+    int rc = pick_variant(H, W, &h->NW, &h->RPL);
+    if (rc != AGV_OK) return rc;
+#define CALL(NW_, RPL_) return launch_warps(k_bfs_field<NW_, RPL_>, B, 0, (cudaStream_t)stream, B, H, W, valid_dev, target_dev, dist_dev)
+    DISPATCH(h, CALL);
+#undef CALL
+}
+
+const char *agv_strerror(int status) {
+    switch (status) {
+        case AGV_OK: return "ok";
+        case AGV_E_INVALID: return "invalid argument";
+        case AGV_E_CUDA: return "CUDA runtime error";
+        case AGV_E_NOMEM: return "out of memory";
+        case AGV_E_UNSUPPORTED: return "size outside the compiled kernel range (H, W <= 128)";
+        case AGV_E_BADGRID: return "grid code outside {0,1,2}";
+        default: return "unknown status";
+    }
+}
+
+int agv_last_cuda_error(void) { return g_last_cuda; }
+uint64_t agv_launch_count(void) { return g_launches.load(); }
+const char *agv_version(void) { return "agv_b200 0.1 (sm_100a)"; }
+
+}  // extern "C"
+
+namespace agv {
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+void note_cuda_error(int e) { g_last_cuda = e; }
+}  // namespace agv

@@ -1,0 +1,346 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and
+the committed live-reference fixtures.  Bit-exact for every integer quantity;
+rewards are compared as float32(reference float64)."""
+import random
+
+import numpy as np
+import pytest
+
+from conftest import golden, load_pkg
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import torch
+    assert torch.cuda.is_available()
+    return load_pkg()
+
+
+def _cmp_tick(pkg, sc, envs, proto, policy, obs_kind, P, given=None, want_next=False, tag=""):
+    out = sc.tick(proto, policy, obs_kind, actions=given, want_next=want_next)
+    act = out["act"].cpu().numpy()
+    rew = out["reward"].cpu().numpy()
+    done = out["done"].cpu().numpy()
+    plen = out["plen"].cpu().numpy().astype(np.int32) & 0xFFFF
+    slen = out["slen"].cpu().numpy().astype(np.int32) & 0xFFFF
+    obs = out["obs"].float().cpu().numpy() if obs_kind else None
+    nxt = out["next_obs"].float().cpu().numpy() if (obs_kind and want_next) else None
+    hdr, agv = sc.get_state()
+    turns = 0
+    for e, env in enumerate(envs):
+        g = None if given is None else np.asarray(given)[e]
+        n, a, r, d, pl, sl, ob, nx = env.tick_obs(proto, policy, given=g, obs_kind=obs_kind, P=P,
+                                                  want_next=want_next)
+        turns += n
+        assert np.array_equal(act[e], a), (tag, e, act[e], a)
+        assert np.array_equal(rew[e], r.astype(np.float32)), (tag, e, rew[e], r)
+        assert np.array_equal(done[e], d), (tag, e)
+        assert np.array_equal(plen[e], pl), (tag, e, plen[e], pl)
+        assert np.array_equal(slen[e], sl), (tag, e, slen[e], sl)
+        if obs is not None:
+            assert np.array_equal(obs[e], ob), (tag, e)
+        if nxt is not None:
+            assert np.array_equal(nxt[e], nx), (tag, e)
+        oh, oa = env.state()
+        assert np.array_equal(hdr[e], oh), (tag, e, hdr[e], oh)
+        assert np.array_equal(agv[e], oa), (tag, e)
+    return turns
+
+
+def test_bfs_fixtures(pkg):
+    """agv_bfs_batch against FindPathAstar outputs recorded from the live reference"""
+    cases = golden("bfs.json")
+    by_shape = {}
+    for c in cases:
+        v = np.array(c["valid"], dtype=np.uint8)
+        by_shape.setdefault(v.shape, []).append((v, c))
+    n = 0
+    for shape, lst in by_shape.items():
+        valid = np.stack([v for v, _ in lst])
+        start = np.array([c["start"] for _, c in lst], dtype=np.int32)
+        target = np.array([c["target"] for _, c in lst], dtype=np.int32)
+        act, ln, fnd = pkg.bfs_batch(valid, start, target)
+        act, ln, fnd = act.cpu().numpy(), ln.cpu().numpy(), fnd.cpu().numpy()
+        for k, (_, c) in enumerate(lst):
+            first = c["actions"][0] if c["actions"] else 4
+            assert act[k] == first and ln[k] == len(c["actions"]) and bool(fnd[k]) == c["found"], (shape, k)
+            n += 1
+    assert n == len(cases)
+
+
+@pytest.mark.parametrize("H,W", [(9, 9), (32, 32), (33, 64), (64, 64), (64, 65), (20, 128), (65, 40), (128, 128),
+                                  (1, 7), (7, 1), (128, 3)])
+def test_bfs_random_vs_oracle(pkg, H, W):
+    rng = np.random.default_rng(H * 1000 + W)
+    B = 96
+    valid = (rng.random((B, H, W)) > rng.choice([0.0, 0.1, 0.25, 0.35], size=(B, 1, 1))).astype(np.uint8)
+    start = np.stack([rng.integers(0, W, B), rng.integers(0, H, B)], axis=1).astype(np.int32)
+    target = np.stack([rng.integers(0, W, B), rng.integers(0, H, B)], axis=1).astype(np.int32)
+    target[:3] = start[:3]
+    act, ln, fnd = pkg.bfs_batch(valid, start, target)
+    act, ln, fnd = act.cpu().numpy(), ln.cpu().numpy(), fnd.cpu().numpy()
+    dist = pkg.bfs_field(valid, target).cpu().numpy()
+    for b in range(B):
+        a, f, l = orc.bfs_field(valid[b], tuple(start[b]), tuple(target[b]))
+        assert (act[b], bool(fnd[b]), ln[b]) == (a, f, l), (b, start[b], target[b])
+        # distance field: 0 at a valid target, monotone along the chosen action
+        tx, ty = target[b]
+        if valid[b, ty, tx]:
+            assert dist[b, ty, tx] == 0
+            if l > 0:
+                sx, sy = start[b]
+                dx, dy = [(0, -1), (1, 0), (0, 1), (-1, 0)][a]
+                assert dist[b, sy + dy, sx + dx] == l - 1
+        else:
+            assert (dist[b] == 0xFFFF).all()
+
+
+@pytest.mark.parametrize("idx", range(7))
+def test_astar_trajectories_fixture(pkg, idx):
+    """Scene.run_game('A_star') trajectories of the live reference"""
+    c = golden("astar_traj.json")[idx]
+    grid = np.array(c["grid"], dtype=np.uint8)
+    tasks = np.array(c["tasks"], dtype=np.uint8)[None]
+    sc = pkg.BatchedScene(grid, 1, c["n_agv"], tasks=tasks)
+    sc.reset()
+    veh, actions = [], []
+    for t in range(c["ticks"] + 2):
+        out = sc.tick(pkg.PROTO_ASTAR, pkg.POLICY_ASTAR)
+        a = out["act"].cpu().numpy()[0]
+        for i in range(c["n_agv"]):
+            if a[i] >= 0:
+                veh.append(i)
+                actions.append(int(a[i]))
+        hdr, agv = sc.get_state()
+        if hdr[0, 5] or (not c["finished"] and hdr[0, 0] >= c["ticks"]):
+            break
+    assert veh == c["veh"] and actions == c["actions"]
+    assert int(hdr[0, 0]) == c["ticks"]
+    snap = [[int(v) for v in agv[0, j, [0, 1, 2, 3, 5]]] for j in range(int(hdr[0, 4]))]
+    assert snap == c["final"]
+
+
+def test_intelligent_fixture_substep(pkg):
+    """the callback protocol (encode -> guidance BFS -> step_turn -> encode) turn by turn
+    against the live-reference recordings: obs, guided action, reward, is_end, snapshots"""
+    eps = golden("intelligent.json")
+    n_turns = n_obs = 0
+    for ep in eps:
+        flags = ep["flags"]
+        grid = np.array(ep["grid"], dtype=np.uint8)
+        N = ep["n_agv"]
+        sc = pkg.BatchedScene(grid, 1, N, tasks=np.array(ep["tasks"], dtype=np.uint8)[None], P=3,
+                              always_loaded=flags.get("Explorer_Always_Loaded", False),
+                              always_empty=flags.get("Explorer_Always_Empty", False),
+                              shaped_reward=flags.get("Sparse_Reward", False), max_steps=ep["max_steps"])
+        sc.reset()
+        turns = ep["turns"]
+        k = 0
+        M = 0.5 * (grid.shape[0] + grid.shape[1])
+        while k < len(turns):
+            sc.begin_tick()
+            ended = False
+            for i in range(N):
+                obs, will = sc.encode(i, pkg.OBS_CLIP)
+                if not int(will.cpu()[0]):
+                    continue
+                t = turns[k]
+                assert t["i"] == i
+                ga, gl = sc.bfs_action(i, pkg.MATRIX_STATE)
+                assert int(ga.cpu()[0]) == t["guided"] and (int(gl.cpu()[0]) & 0xFFFF) == t["glen"]
+                if "obs_clip" in t:
+                    assert obs.float().cpu().numpy()[0].astype(int).tolist() == t["obs_clip"]
+                    of, _ = sc.encode(i, pkg.OBS_FULL)
+                    assert of.float().cpu().numpy()[0].astype(int).tolist() == t["obs_full"]
+                    n_obs += 1
+                rew, done, acted, slen = sc.step_turn(i, pkg.PROTO_INTELLIGENT, np.array([t["a"]], dtype=np.int8))
+                assert int(acted.cpu()[0]) == 1
+                r = float(rew.cpu()[0])
+                sl = int(slen.cpu()[0]) & 0xFFFF
+                if sl != 0xFFFF:  # shaped reward: rebuild the float64 value exactly like Explorer.py:243-248
+                    assert 0.001 * (M - sl) / M == t["r"]
+                    assert r == np.float32(t["r"])
+                else:
+                    assert r == t["r"]
+                assert int(done.cpu()[0]) == t["end"]
+                hdr, agv = sc.get_state()
+                snap = [[int(v) for v in agv[0, j, [0, 1, 2, 3, 5]]] for j in range(int(hdr[0, 4]))]
+                assert snap == t["after"], (ep["ep"], k)
+                k += 1
+                n_turns += 1
+                if t["end"]:
+                    ended = True
+                    break
+            if ended:
+                break
+            sc.end_tick()
+        assert k == len(turns)
+        if ep["running_time"] >= 0:
+            assert int(sc.get_state()[0][0, 0]) == ep["running_time"]
+        sc.close()
+    assert n_turns > 6000 and n_obs > 50
+
+
+def test_intelligent_fixture_fused_given(pkg):
+    """same recordings through the fused tick with the recorded actions"""
+    eps = golden("intelligent.json")
+    for ep in eps[::3]:
+        flags = ep["flags"]
+        grid = np.array(ep["grid"], dtype=np.uint8)
+        N = ep["n_agv"]
+        kw = dict(always_loaded=flags.get("Explorer_Always_Loaded", False),
+                  always_empty=flags.get("Explorer_Always_Empty", False),
+                  shaped=flags.get("Sparse_Reward", False), max_steps=ep["max_steps"])
+        sc = pkg.BatchedScene(grid, 1, N, tasks=np.array(ep["tasks"], dtype=np.uint8)[None], P=3,
+                              always_loaded=kw["always_loaded"], always_empty=kw["always_empty"],
+                              shaped_reward=kw["shaped"], max_steps=ep["max_steps"])
+        sc.reset()
+        turns = ep["turns"]
+        k = 0
+        while k < len(turns):
+            given = np.full((1, N), 4, dtype=np.int8)
+            kk, last = k, -1
+            while kk < len(turns) and turns[kk]["i"] > last:
+                given[0, turns[kk]["i"]] = turns[kk]["a"]
+                last = turns[kk]["i"]
+                kk += 1
+            out = sc.tick(pkg.PROTO_INTELLIGENT, pkg.POLICY_GIVEN, actions=given)
+            act = out["act"].cpu().numpy()[0]
+            rew = out["reward"].cpu().numpy()[0]
+            done = out["done"].cpu().numpy()[0]
+            for i in range(N):
+                if act[i] >= 0:
+                    t = turns[k]
+                    assert (t["i"], t["a"]) == (i, act[i])
+                    assert rew[i] == np.float32(t["r"]) and done[i] == t["end"]
+                    k += 1
+            if sc.get_state()[0][0, 5]:
+                break
+        assert k == len(turns)
+        sc.close()
+
+
+CASES = [
+    # name, grid, N, E, ticks, proto, policy, obs_kind, flags
+    ("c1_guided_clip", lambda: orc.rect_layout(4, 2, 2, 2, 2), 4, 16, 120, 1, 2, 1, {}),
+    ("c2_guided_full", lambda: orc.README_9x9, 4, 16, 100, 1, 2, 2, {}),
+    ("c1_astar", lambda: orc.rect_layout(4, 2, 2, 2, 2), 6, 8, 150, 0, 1, 1, {}),
+    ("c3_guided_clip", lambda: orc.rect_layout(6, 2, 9, 20, 8), 64, 6, 140, 1, 2, 1, {}),
+    ("c3_astar_full", lambda: orc.rect_layout(6, 2, 9, 20, 8), 40, 3, 60, 0, 1, 2, {}),
+    ("c3_shaped", lambda: orc.rect_layout(6, 2, 9, 20, 8), 24, 4, 60, 1, 2, 1, {"shaped": True}),
+    ("wide_128", lambda: orc.rect_layout(6, 2, 18, 41, 9), 48, 3, 100, 1, 2, 1, {}),
+    ("tall_40x128", lambda: orc.rect_layout(2, 2, 13, 41, 3), 33, 3, 80, 1, 2, 1, {}),
+    ("always_loaded", lambda: orc.rect_layout(3, 2, 3, 3, 2), 5, 8, 80, 1, 2, 1, {"always_loaded": True}),
+    ("always_empty", lambda: orc.rect_layout(3, 2, 3, 3, 2), 5, 8, 80, 1, 2, 2, {"always_empty": True}),
+    ("single_agv", lambda: orc.rect_layout(3, 2, 2, 2, 2), 1, 8, 200, 1, 2, 1, {}),
+    ("more_agv_than_tasks", lambda: orc.rect_layout(1, 1, 2, 1, 1), 6, 8, 80, 0, 1, 1, {}),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_fused_tick_vs_oracle(pkg, case):
+    name, gridf, N, E, ticks, proto, policy, obs_kind, flags = case
+    grid = gridf()
+    assert grid.shape[0] <= 128 and grid.shape[1] <= 128
+    tasks = np.array([orc.make_tasks(grid, random.Random(100 + e)) for e in range(E)], dtype=np.uint8)
+    sc = pkg.BatchedScene(grid, E, N, tasks=tasks, P=3, always_loaded=flags.get("always_loaded", False),
+                          always_empty=flags.get("always_empty", False), shaped_reward=flags.get("shaped", False))
+    sc.reset()
+    envs = [orc.Env(grid, tasks[e], N, always_loaded=flags.get("always_loaded", False),
+                    always_empty=flags.get("always_empty", False), shaped=flags.get("shaped", False))
+            for e in range(E)]
+    turns = 0
+    for t in range(ticks):
+        # restart finished / failed scenes so that the run keeps exercising turns
+        hdr, _ = sc.get_state()
+        over = hdr[:, 5].astype(bool)
+        if over.any():
+            sc.reset(over.astype(np.uint8))
+            for e in np.nonzero(over)[0]:
+                envs[e].reset()
+        turns += _cmp_tick(pkg, sc, envs, proto, policy, obs_kind, 3, want_next=(t % 3 == 0), tag=(name, t))
+    assert turns > ticks
+    c_turns, c_eps, c_bad = sc.counters()
+    assert c_turns == turns and c_bad == 0
+    sc.close()
+
+
+def test_fused_given_random_actions_vs_oracle(pkg):
+    """random (mostly illegal) open-loop actions incl. the guided fallback (-1) and STOP"""
+    grid = orc.rect_layout(4, 2, 2, 2, 2)
+    E, N = 32, 4
+    rng = np.random.default_rng(3)
+    tasks = np.array([orc.make_tasks(grid, random.Random(e)) for e in range(E)], dtype=np.uint8)
+    for proto in (0, 1):
+        sc = pkg.BatchedScene(grid, E, N, tasks=tasks, P=2)
+        sc.reset()
+        envs = [orc.Env(grid, tasks[e], N) for e in range(E)]
+        for t in range(150):
+            hdr, _ = sc.get_state()
+            over = hdr[:, 5].astype(bool)
+            if over.any():
+                sc.reset(over.astype(np.uint8))
+                for e in np.nonzero(over)[0]:
+                    envs[e].reset()
+            given = rng.choice(np.array([-1, -1, -1, -1, -1, -1, 0, 1, 2, 3, 4], dtype=np.int8), size=(E, N))
+            _cmp_tick(pkg, sc, envs, proto, 0, 1, 2, given=given, want_next=True, tag=("given", proto, t))
+        sc.close()
+
+
+def test_auto_reset_and_substep_equals_fused(pkg):
+    """auto_reset=1: sub-step protocol (begin/encode/bfs/step/end) == fused guided tick"""
+    grid = orc.README_9x9
+    E, N = 24, 4
+    tasks = np.array([orc.make_tasks(grid, random.Random(7 * e)) for e in range(E)], dtype=np.uint8)
+    a = pkg.BatchedScene(grid, E, N, tasks=tasks, auto_reset=True)
+    b = pkg.BatchedScene(grid, E, N, tasks=tasks, auto_reset=True)
+    a.reset()
+    b.reset()
+    import torch
+    for t in range(120):
+        out = a.tick(pkg.PROTO_INTELLIGENT, pkg.POLICY_GUIDED, pkg.OBS_CLIP, want_next=True)
+        b.begin_tick()
+        for k in range(N):
+            obs, will = b.encode(k, pkg.OBS_CLIP)
+            act, plen = b.bfs_action(k, pkg.MATRIX_STATE)
+            assert torch.equal(obs, out["obs"][:, k])
+            assert torch.equal(act, out["act"][:, k])
+            rew, done, acted, slen = b.step_turn(k, pkg.PROTO_INTELLIGENT, act.clamp(min=0))
+            assert torch.equal(acted.bool(), out["act"][:, k] >= 0)
+            assert torch.equal(rew, out["reward"][:, k]) and torch.equal(done, out["done"][:, k])
+            nobs, did = b.encode(k, pkg.OBS_CLIP, post=True)
+            assert torch.equal(nobs, out["next_obs"][:, k])
+        b.end_tick()
+        ha, ga = a.get_state()
+        hb, gb = b.get_state()
+        assert np.array_equal(ha, hb) and np.array_equal(ga, gb)
+    assert a.counters()[1] > 0  # some episodes ended and were auto-reset
+    a.close()
+    b.close()
+
+
+def test_invalid_arguments(pkg):
+    import ctypes as C
+    L = pkg._lib
+    lib = L.lib()
+    grid = np.zeros((4, 4), dtype=np.uint8)
+    h = C.c_void_p()
+    cfg = L.AgvConfig(H=4, W=4, E=1, N=65, T=0, P=3, max_steps=10, device=0)
+    assert lib.agv_create(C.byref(cfg), grid.ctypes.data_as(C.c_void_p), C.byref(h)) == -1
+    cfg = L.AgvConfig(H=200, W=4, E=1, N=1, T=0, P=3, max_steps=10, device=0)
+    assert lib.agv_create(C.byref(cfg), grid.ctypes.data_as(C.c_void_p), C.byref(h)) == -4
+    bad = grid.copy()
+    bad[1, 1] = 3
+    cfg = L.AgvConfig(H=4, W=4, E=1, N=1, T=0, P=3, max_steps=10, device=0)
+    assert lib.agv_create(C.byref(cfg), bad.ctypes.data_as(C.c_void_p), C.byref(h)) == -5
+    # invalid action codes are data: counted and treated as STOP, never a crash
+    sc = pkg.BatchedScene(orc.rect_layout(2, 1, 1, 1, 1), 2, 1, tasks=np.array([[[2, 2, 2, 4], [3, 2, 2, 4]]] * 2))
+    sc.reset()
+    sc.tick(pkg.PROTO_INTELLIGENT, pkg.POLICY_GIVEN, actions=np.full((2, 1), 9, dtype=np.int8))
+    assert sc.counters()[2] == 2
+    with pytest.raises(L.AgvError):
+        sc.set_tasks(np.zeros((2, 2, 4), dtype=np.uint8))  # coordinates out of range
+    sc.close()
