@@ -268,10 +268,10 @@ def main():
         step()
     torch.cuda.synchronize()
 
+    du = importlib.import_module(PKG + ".dist_util")
+
     def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        du.barrier(dev)
 
     def timed(fn, k):
         """k calls bracketed by barrier + synchronize, CUDA events on the launching stream;
@@ -288,12 +288,7 @@ def main():
         ms = ev0.elapsed_time(ev1)
         turns = sc.counters()[0]
         launches = lib.agv_launch_count() - l0
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            n = torch.tensor([turns], dtype=torch.float64, device=dev)
-            dist.all_reduce(n, op=dist.ReduceOp.SUM)
-            ms, turns = float(t.item()), int(n.item())
+        ms, turns = du.reduce_timing(ms, turns, dev)
         return ms, turns, launches
 
     for _ in range(warmup):

@@ -180,9 +180,14 @@ int agv_replay_push(AgvReplay *r, int64_t n_rows, const int8_t *act_dev, const f
                     const double *priority_dev, void *stream);
 /* Memory.sample(n) (PER.py:86-108) with the n uniforms injected: u01_dev float64[n]
  * in [0,1); s_i = seg*i + seg*u_i, sum-tree descent.  Writes the chosen data slots
- * (int64[n]) and gathers the batch. */
-int agv_replay_sample(AgvReplay *r, int32_t n, const double *u01_dev, int64_t *slot_dev, void *obs_dev,
-                      int8_t *act_dev, float *reward_dev, void *next_obs_dev, uint8_t *done_dev, void *stream);
+ * (int64[n]), their priorities tree[idx] (float64[n], optional) and gathers the batch. */
+int agv_replay_sample(AgvReplay *r, int32_t n, const double *u01_dev, int64_t *slot_dev, double *prio_dev,
+                      void *obs_dev, int8_t *act_dev, float *reward_dev, void *next_obs_dev, uint8_t *done_dev,
+                      void *stream);
+/* Memory.update (PER.py:110-112) / SumTree.update (55-59) for n tree indices
+ * (tree_idx = slot + capacity - 1, as returned by Memory.sample), applied in order. */
+int agv_replay_update(AgvReplay *r, int32_t n, const int64_t *tree_idx_dev, const double *priority_dev,
+                      void *stream);
 /* uniform gather by explicit slots (int64[n]) */
 int agv_replay_gather(AgvReplay *r, int32_t n, const int64_t *slot_dev, void *obs_dev, int8_t *act_dev,
                       float *reward_dev, void *next_obs_dev, uint8_t *done_dev, void *stream);

@@ -10,5 +10,15 @@ from . import _lib
 from ._lib import (AgvError, UP, RIGHT, DOWN, LEFT, STOP, NO_TURN, PROTO_ASTAR, PROTO_INTELLIGENT, POLICY_GIVEN,
                    POLICY_ASTAR, POLICY_GUIDED, MATRIX_ASTAR, MATRIX_STATE, OBS_NONE, OBS_CLIP, OBS_FULL)
 from .batched import BatchedScene, bfs_batch, bfs_field, max_training_steps
+from .replay import DeviceReplay
+from .multiAGVscene import Layout, Explorer, Scene
+from .algorithm.Manager.StateManager import StateManager
+from .algorithm.Manager.ExpertManager import Expert
+from .algorithm.MADQN_structure.PER import Memory, SumTree
+from .utils.astar import FindPathAstar
+from .utils.utils import Direction
+from .utils.settings import SuperParas
 
-__all__ = ["BatchedScene", "bfs_batch", "bfs_field", "max_training_steps", "AgvError"]
+__all__ = ["BatchedScene", "DeviceReplay", "bfs_batch", "bfs_field", "max_training_steps", "AgvError", "Layout",
+           "Explorer", "Scene", "StateManager", "Expert", "Memory", "SumTree", "FindPathAstar", "Direction",
+           "SuperParas"]

@@ -47,7 +47,8 @@ SYMBOLS = {
     "agv_replay_create": (C.c_int, [_i32, _i64, _i32, C.POINTER(_vp)]),
     "agv_replay_destroy": (C.c_int, [_vp]),
     "agv_replay_push": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "agv_replay_sample": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "agv_replay_sample": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "agv_replay_update": (C.c_int, [_vp, _i32, _vp, _vp, _vp]),
     "agv_replay_gather": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "agv_replay_info": (C.c_int, [_vp, _vp, _vp, _vp]),
     "agv_strerror": (C.c_char_p, [C.c_int]),

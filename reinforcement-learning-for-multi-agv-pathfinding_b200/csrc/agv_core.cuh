@@ -181,61 +181,87 @@ __device__ __forceinline__ bool test_bit_local(const Row<NW> (&rows)[RPL], int r
 // (neighbour order astar.py:33-38); hence the priority RIGHT, DOWN, UP, LEFT
 // among start neighbours one step closer to the target.
 // Coordinates are 0-based.  All lanes must call; the result is warp-uniform.
+// multiply both 32-bit halves by m in {0,1}: boundary masking on the FMA pipe (IMAD)
+// instead of SEL on the (saturated) ALU pipe
+template <int NW>
+__device__ __forceinline__ Row<NW> rmask01(const Row<NW> &a, uint32_t m) {
+    Row<NW> r;
+#pragma unroll
+    for (int i = 0; i < NW; i++) {
+        const uint32_t lo = (uint32_t)a.w[i] * m, hi = (uint32_t)(a.w[i] >> 32) * m;
+        r.w[i] = ((uint64_t)hi << 32) | lo;
+    }
+    return r;
+}
+
+// one BFS level: f <- neighbours(f) & av;  av <- av & ~f   (av = valid & ~visited)
+template <int NW, int RPL>
+__device__ __forceinline__ void bfs_expand(Row<NW> (&f)[RPL], Row<NW> (&av)[RPL], uint32_t m_up, uint32_t m_dn) {
+    // Lane 0 (31) gets its OWN register back from shfl_up (shfl_down).  For RPL <= 2 that
+    // row is either the frontier row itself (f & av == 0) or a true vertical neighbour that
+    // is OR-ed in anyway, so no boundary masking is needed; RPL > 2 masks explicitly.
+    Row<NW> up_in = rshfl_up(f[RPL - 1]);
+    Row<NW> dn_in = rshfl_down(f[0]);
+    if (RPL > 2) { up_in = rmask01(up_in, m_up); dn_in = rmask01(dn_in, m_dn); }
+    Row<NW> n[RPL];
+#pragma unroll
+    for (int s = 0; s < RPL; s++) {
+        Row<NW> a = ror(rshl1(f[s]), rshr1(f[s]));
+        const Row<NW> u = (s > 0) ? f[s > 0 ? s - 1 : 0] : up_in;
+        const Row<NW> d = (s < RPL - 1) ? f[s < RPL - 1 ? s + 1 : 0] : dn_in;
+        a = ror(a, u);
+        n[s] = rand_(ror(a, d), av[s]);
+    }
+#pragma unroll
+    for (int s = 0; s < RPL; s++) { av[s] = randn(av[s], n[s]); f[s] = n[s]; }
+}
+
 template <int NW, int RPL>
 __device__ __forceinline__ int warp_bfs(const Row<NW> (&valid)[RPL], int sx, int sy, int tx, int ty, int H, int W,
                                         int lane, int &len) {
     len = 0;
     if (sx == tx && sy == ty) return A_STOP;  // found, empty action list (astar.py:90-92)
-    Row<NW> f[RPL], vis[RPL], nb[RPL];
+    Row<NW> f[RPL], av[RPL], nb[RPL];
 #pragma unroll
     for (int s = 0; s < RPL; s++) { f[s] = rzero<NW>(); nb[s] = rzero<NW>(); }
     set_bit<NW, RPL>(f, ty, tx, lane);
 #pragma unroll
-    for (int s = 0; s < RPL; s++) { f[s] = rand_(f[s], valid[s]); vis[s] = f[s]; }
+    for (int s = 0; s < RPL; s++) { f[s] = rand_(f[s], valid[s]); av[s] = randn(valid[s], f[s]); }
     if (sx + 1 < W) set_bit<NW, RPL>(nb, sy, sx + 1, lane);
     if (sy + 1 < H) set_bit<NW, RPL>(nb, sy + 1, sx, lane);
     if (sy - 1 >= 0) set_bit<NW, RPL>(nb, sy - 1, sx, lane);
     if (sx - 1 >= 0) set_bit<NW, RPL>(nb, sy, sx - 1, lane);
-    const int max_level = H * W;
-    for (int level = 0; level <= max_level; ++level) {
-        unsigned fl = 0;
+    const uint32_t m_up = lane != 0 ? 1u : 0u, m_dn = lane != 31 ? 1u : 0u;
+    int level = 0;
+    for (;;) {
 #pragma unroll
-        for (int s = 0; s < RPL; s++) {
-            fl |= rany(f[s]) ? 1u : 0u;
-            fl |= rany(rand_(f[s], nb[s])) ? 2u : 0u;
-        }
-        const unsigned red = __reduce_or_sync(FULL, fl);
-        if (red & 2u) {
-            unsigned code = 0;
-            if (sx + 1 < W && test_bit_local<NW, RPL>(f, sy, sx + 1, lane)) code |= 1u;
-            if (sy + 1 < H && test_bit_local<NW, RPL>(f, sy + 1, sx, lane)) code |= 2u;
-            if (sy - 1 >= 0 && test_bit_local<NW, RPL>(f, sy - 1, sx, lane)) code |= 4u;
-            if (sx - 1 >= 0 && test_bit_local<NW, RPL>(f, sy, sx - 1, lane)) code |= 8u;
-            code = __reduce_or_sync(FULL, code);
-            len = level + 1;
-            if (code & 1u) return A_RIGHT;
-            if (code & 2u) return A_DOWN;
-            if (code & 4u) return A_UP;
-            return A_LEFT;
-        }
-        if (!(red & 1u)) return A_STOP;  // frontier empty: target unreachable
-        Row<NW> up_in = rshfl_up(f[RPL - 1]);
-        Row<NW> dn_in = rshfl_down(f[0]);
-        if (lane == 0) up_in = rzero<NW>();
-        if (lane == 31) dn_in = rzero<NW>();
-        Row<NW> n[RPL];
+        for (int u = 0; u < 4; u++) {
+            bool hit = false;
 #pragma unroll
-        for (int s = 0; s < RPL; s++) {
-            Row<NW> a = ror(rshl1(f[s]), rshr1(f[s]));
-            Row<NW> u = (s > 0) ? f[s > 0 ? s - 1 : 0] : up_in;
-            Row<NW> d = (s < RPL - 1) ? f[s < RPL - 1 ? s + 1 : 0] : dn_in;
-            a = ror(a, ror(u, d));
-            n[s] = rand_(a, randn(valid[s], vis[s]));
+            for (int s = 0; s < RPL; s++) hit |= rany(rand_(f[s], nb[s]));
+            if (__any_sync(FULL, hit)) {
+                unsigned code = 0;
+                if (sx + 1 < W && test_bit_local<NW, RPL>(f, sy, sx + 1, lane)) code |= 1u;
+                if (sy + 1 < H && test_bit_local<NW, RPL>(f, sy + 1, sx, lane)) code |= 2u;
+                if (sy - 1 >= 0 && test_bit_local<NW, RPL>(f, sy - 1, sx, lane)) code |= 4u;
+                if (sx - 1 >= 0 && test_bit_local<NW, RPL>(f, sy, sx - 1, lane)) code |= 8u;
+                code = __reduce_or_sync(FULL, code);
+                len = level + 1;
+                if (code & 1u) return A_RIGHT;
+                if (code & 2u) return A_DOWN;
+                if (code & 4u) return A_UP;
+                return A_LEFT;
+            }
+            bfs_expand<NW, RPL>(f, av, m_up, m_dn);
+            ++level;
         }
+        // the frontier-empty test (target unreachable) is amortised over 4 levels: an empty
+        // frontier stays empty, so at most 3 extra no-op levels are expanded
+        bool ne = false;
 #pragma unroll
-        for (int s = 0; s < RPL; s++) { vis[s] = ror(vis[s], n[s]); f[s] = n[s]; }
+        for (int s = 0; s < RPL; s++) ne |= rany(f[s]);
+        if (!__any_sync(FULL, ne)) return A_STOP;
     }
-    return A_STOP;
 }
 
 // Full distance field from the target (uint16, 0xFFFF unreachable) into dist[H*W]
@@ -491,9 +517,11 @@ struct WarpScene {
     }
 
     // StateManager.create_state(obs_clip=True) (StateManager.py:14-41,145-192) into a
-    // [3,K,K] bf16 record in shared memory; vrow_s holds matrix (b).
-    __device__ __forceinline__ void encode_clip(uint16_t *dst, const Agv &a) const {
-        const int P = c.P, K = c.K, KK = K * K, n = 3 * KK;
+    // [3,K,K] bf16 record in shared memory; vrow_s holds matrix (b).  KT > 0 fixes K at
+    // compile time (the index divisions become multiplies).
+    template <int KT>
+    __device__ __forceinline__ void encode_clip_impl(uint16_t *dst, const Agv &a) const {
+        const int K = KT > 0 ? KT : c.K, P = (K - 1) >> 1, KK = K * K, n = 3 * KK;
         const int cx = a.x - 1, cy = a.y - 1;
         int tdx = a.tx - a.x, tdy = a.ty - a.y;
         tdx = max(-P, min(P, tdx)) + P;
@@ -510,6 +538,10 @@ struct WarpScene {
             }
             dst[idx] = v ? BF16_ONE : (uint16_t)0;
         }
+    }
+    __device__ __forceinline__ void encode_clip(uint16_t *dst, const Agv &a) const {
+        if (c.K == 7) encode_clip_impl<7>(dst, a);
+        else encode_clip_impl<0>(dst, a);
     }
     // StateManager.create_state(obs_clip=False) straight to a [3,H,W] bf16 record in HBM
     __device__ __forceinline__ void encode_full(uint16_t *dst, const Agv &a) const {

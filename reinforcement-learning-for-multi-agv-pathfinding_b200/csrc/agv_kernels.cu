@@ -54,8 +54,12 @@ struct StepArgs {
     ws.hdr_to_regs();
 
 // ---------------------------------------------------------------- fused tick
+// resident CTAs per SM the register budget is tuned for (ptxas -v: no spills at these bounds)
 template <int NW, int RPL>
-__global__ void __launch_bounds__(128) k_tick(const DevCfg c, const TickArgs t) {
+constexpr int tick_min_blocks() { return NW * RPL <= 2 ? 6 : (NW * RPL <= 4 ? 4 : 2); }
+
+template <int NW, int RPL>
+__global__ void __launch_bounds__(128, tick_min_blocks<NW, RPL>()) k_tick(const DevCfg c, const TickArgs t) {
     WARP_PROLOGUE(t)
     int8_t *o_act = reinterpret_cast<int8_t *>(wbase + t.off_act);
     uint8_t *o_done = wbase + t.off_done;
@@ -87,8 +91,8 @@ __global__ void __launch_bounds__(128) k_tick(const DevCfg c, const TickArgs t) 
         const size_t rec = (size_t)e * N + i;
         uint16_t *od = nullptr, *nd = nullptr;
         if (clip) {
-            if (t.obs) od = stage + (size_t)(i % G) * R;
-            if (t.next_obs) nd = stage2 + (size_t)(i % G) * R;
+            if (t.obs) od = stage + (size_t)(i & (G - 1)) * R;
+            if (t.next_obs) nd = stage2 + (size_t)(i & (G - 1)) * R;
         } else if (full) {
             if (t.obs) od = t.obs + rec * R;
             if (t.next_obs) nd = t.next_obs + rec * R;
@@ -111,8 +115,8 @@ __global__ void __launch_bounds__(128) k_tick(const DevCfg c, const TickArgs t) 
                 if (nd) zero_global(nd, R, lane);
             }
         }
-        if (clip && (((i + 1) % G) == 0 || i == N - 1)) {
-            const int g0 = i - (i % G), nrec = i - g0 + 1;
+        if (clip && (((i + 1) & (G - 1)) == 0 || i == N - 1)) {  // G is a power of two
+            const int g0 = i & ~(G - 1), nrec = i - g0 + 1;
             const size_t off = ((size_t)e * N + g0) * R;
             if (t.obs) flush_bytes(reinterpret_cast<uint8_t *>(t.obs + off), reinterpret_cast<uint8_t *>(stage),
                                    nrec * R * 2, lane);
@@ -358,6 +362,10 @@ static int launch_warps(K kernel, int n_warps, size_t smem_per_warp, cudaStream_
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { g_last_cuda = (int)e; return AGV_E_CUDA; }
     }
+    if (smem > 0) {
+        // the scenes live in shared memory and nothing is re-read through L1: give smem the carveout
+        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    }
     kernel<<<ctas, WARPS_PER_CTA * 32, smem, st>>>(args...);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
@@ -506,8 +514,8 @@ int agv_tick(AgvHandle *h, int32_t proto, int32_t policy, int32_t obs_kind, cons
     t.off_slen = off; off += align16(2 * N);
     t.off_rew = off; off += align16(4 * N);
     const int stage_bytes = (t.obs_kind == AGV_OBS_CLIP) ? align16(t.group * t.rec_elems * 2) : 0;
-    t.off_stage = off; off += stage_bytes;
-    t.off_stage2 = off; off += stage_bytes;
+    t.off_stage = off; off += t.obs ? stage_bytes : 0;
+    t.off_stage2 = off; off += t.next_obs ? stage_bytes : 0;
     t.per_warp = off;
 #define CALL(NW_, RPL_) return launch_warps(k_tick<NW_, RPL_>, h->cfg.E, t.per_warp, (cudaStream_t)stream, h->dc, t)
     DISPATCH(h, CALL);

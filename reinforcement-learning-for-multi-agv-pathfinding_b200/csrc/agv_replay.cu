@@ -186,8 +186,8 @@ __device__ __forceinline__ void gather_row(const ReplayDev &r, long long s, int 
 }
 
 // Memory.sample (PER.py:86-108): one warp per sample; lane 0 walks the tree.
-__global__ void k_sample(ReplayDev r, int n, const double *u01, long long *slot_out, uint16_t *obs, int8_t *act,
-                         float *rew, uint16_t *next_obs, uint8_t *done) {
+__global__ void k_sample(ReplayDev r, int n, const double *u01, long long *slot_out, double *prio_out, uint16_t *obs,
+                         int8_t *act, float *rew, uint16_t *next_obs, uint8_t *done) {
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= n) return;
@@ -207,9 +207,26 @@ __global__ void k_sample(ReplayDev r, int n, const double *u01, long long *slot_
         }
         slot = idx - r.cap + 1;
         if (slot_out) slot_out[q] = slot;
+        if (prio_out) prio_out[q] = r.tree[idx];
     }
     slot = __shfl_sync(0xffffffffu, slot, 0);
     gather_row(r, slot, q, obs, act, rew, next_obs, done, lane);
+}
+
+// SumTree.update (PER.py:55-59) for a list of tree indices, sequentially (reference order)
+__global__ void k_tree_update_list(ReplayDev r, int n, const long long *tree_idx, const double *prio) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const long long nn = 2 * r.cap - 1;
+    for (int t = 0; t < n; t++) {
+        long long idx = tree_idx[t];
+        if (idx < 0 || idx >= nn) continue;
+        const double change = prio[t] - r.tree[idx];
+        r.tree[idx] = prio[t];
+        while (idx != 0) {
+            idx = (idx - 1) / 2;
+            r.tree[idx] += change;
+        }
+    }
 }
 
 __global__ void k_gather(ReplayDev r, int n, const long long *slots, uint16_t *obs, int8_t *act, float *rew,
@@ -337,13 +354,23 @@ int agv_replay_push(AgvReplay *r, int64_t n_rows, const int8_t *act_dev, const f
     return AGV_OK;
 }
 
-int agv_replay_sample(AgvReplay *r, int32_t n, const double *u01_dev, int64_t *slot_dev, void *obs_dev,
-                      int8_t *act_dev, float *reward_dev, void *next_obs_dev, uint8_t *done_dev, void *stream) {
+int agv_replay_sample(AgvReplay *r, int32_t n, const double *u01_dev, int64_t *slot_dev, double *prio_dev,
+                      void *obs_dev, int8_t *act_dev, float *reward_dev, void *next_obs_dev, uint8_t *done_dev,
+                      void *stream) {
     if (!r || n < 1 || !u01_dev) return AGV_E_INVALID;
     R_TRY(cudaSetDevice(r->device));
-    k_sample<<<(n + 3) / 4, 128, 0, (cudaStream_t)stream>>>(r->d, n, u01_dev, (long long *)slot_dev,
+    k_sample<<<(n + 3) / 4, 128, 0, (cudaStream_t)stream>>>(r->d, n, u01_dev, (long long *)slot_dev, prio_dev,
                                                            (uint16_t *)obs_dev, act_dev, reward_dev,
                                                            (uint16_t *)next_obs_dev, done_dev);
+    R_LAUNCH_CHECK();
+    return AGV_OK;
+}
+
+int agv_replay_update(AgvReplay *r, int32_t n, const int64_t *tree_idx_dev, const double *priority_dev,
+                      void *stream) {
+    if (!r || n < 1 || !tree_idx_dev || !priority_dev) return AGV_E_INVALID;
+    R_TRY(cudaSetDevice(r->device));
+    k_tree_update_list<<<1, 32, 0, (cudaStream_t)stream>>>(r->d, n, (const long long *)tree_idx_dev, priority_dev);
     R_LAUNCH_CHECK();
     return AGV_OK;
 }

@@ -164,8 +164,36 @@ def gen_per():
     dump("per.json", out)
 
 
+def gen_expert_csv():
+    """ExpertManager.create_data_by_self of the live reference -> tests/golden/expert_ref_*.csv"""
+    import contextlib, io, signal, shutil, importlib
+    rh.load()
+    EM = importlib.import_module("src.algorithm.Manager.ExpertManager")
+    meta = []
+    for tag, rect, n, seed, times in (("a", (2, 1, 2, 1, 1), 1, 11, 3), ("b", (2, 2, 2, 1, 2), 2, 4, 2)):
+        random.seed(seed)
+        scene = rh.make_scene(n, rect=rect, flags={})   # make_scene(seed=None) keeps the stream
+        tmp = "/tmp/_expert_ref_%s.csv" % tag
+        if os.path.exists(tmp):
+            os.remove(tmp)
+        ex = EM.Expert(scene, *rect, n, filename=tmp)
+        orig = scene.run_game
+        scene.run_game = lambda control_pattern="A_star", **kw: orig(control_pattern=control_pattern, render=False)
+        signal.alarm(60)
+        with contextlib.redirect_stdout(io.StringIO()):
+            ex.create_data_by_self(times=times)
+        signal.alarm(0)
+        dst = os.path.join(HERE, "expert_ref_%s.csv" % tag)
+        shutil.copy(tmp, dst)
+        meta.append({"tag": tag, "rect": list(rect), "n_agv": n, "seed": seed, "times": times,
+                     "bytes": os.path.getsize(dst)})
+        print("wrote", dst, os.path.getsize(dst))
+    dump("expert_ref_meta.json", meta)
+
+
 if __name__ == "__main__":
     gen_bfs()
     gen_astar_traj()
     gen_intelligent()
     gen_per()
+    gen_expert_csv()
