@@ -204,15 +204,17 @@ def test_replay_large_push_and_gather(pkg):
         a, r, d, o, o2 = store[int(s)]
         assert int(b["act"][q]) == a and float(b["reward"][q]) == r and int(b["done"][q]) == d
         assert np.array_equal(b["obs"][q].float().cpu().numpy(), o) and np.array_equal(b["next_obs"][q].float().cpu().numpy(), o2)
-    # stratified sampling lands in the right prefix-sum interval
+    # stratified sampling == the reference's descent (PER.py:25-35) on the same heap-layout tree
+    # (for a capacity that is not a power of two the leaves are NOT in slot order)
     u = rng.random(64)
     sb = rp.sample(64, u)
-    cs = np.cumsum(tree)
-    seg = total / 64
-    for q in range(64):
-        s = seg * q + seg * u[q]
-        slot = int(sb["slot"][q])
-        assert cs[slot] >= s - 1e-6 and (cs[slot] - tree[slot]) <= s + 1e-6
+    ot = orc.SumTree(cap)
+    ot.tree[cap - 1:] = tree
+    for v in range(cap - 2, -1, -1):
+        ot.tree[v] = ot.tree[2 * v + 1] + ot.tree[2 * v + 2]
+    slots_ref, _, prio_ref = orc.per_sample(ot, 64, u)
+    assert sb["slot"].cpu().numpy().tolist() == slots_ref.tolist()
+    assert np.array_equal(sb["prio"].cpu().numpy(), prio_ref)
     rp.close()
 
 
