@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libagv_b200.so")
+LIB_PATH = os.environ.get("AGV_B200_LIB", os.path.join(HERE, "libagv_b200.so"))  # override = tuning builds
 
 OK = 0
 UP, RIGHT, DOWN, LEFT, STOP, NO_TURN = 0, 1, 2, 3, 4, -1

@@ -194,6 +194,21 @@ __device__ __forceinline__ Row<NW> rmask01(const Row<NW> &a, uint32_t m) {
     return r;
 }
 
+// a & ~b for b a subset of a, as per-half a + b * 0xffffffff: mad.lo.u32 issues on the FMA
+// pipe (IMAD), off-loading the ALU pipe that bounds the BFS level loop
+template <int NW>
+__device__ __forceinline__ Row<NW> rsub_subset(const Row<NW> &a, const Row<NW> &b) {
+    Row<NW> r;
+#pragma unroll
+    for (int i = 0; i < NW; i++) {
+        uint32_t lo, hi;
+        asm("mad.lo.u32 %0, %1, 0xffffffff, %2;" : "=r"(lo) : "r"((uint32_t)b.w[i]), "r"((uint32_t)a.w[i]));
+        asm("mad.lo.u32 %0, %1, 0xffffffff, %2;" : "=r"(hi) : "r"((uint32_t)(b.w[i] >> 32)), "r"((uint32_t)(a.w[i] >> 32)));
+        r.w[i] = ((uint64_t)hi << 32) | lo;
+    }
+    return r;
+}
+
 // one BFS level: f <- neighbours(f) & av;  av <- av & ~f   (av = valid & ~visited)
 template <int NW, int RPL>
 __device__ __forceinline__ void bfs_expand(Row<NW> (&f)[RPL], Row<NW> (&av)[RPL], uint32_t m_up, uint32_t m_dn) {
@@ -213,7 +228,7 @@ __device__ __forceinline__ void bfs_expand(Row<NW> (&f)[RPL], Row<NW> (&av)[RPL]
         n[s] = rand_(ror(a, d), av[s]);
     }
 #pragma unroll
-    for (int s = 0; s < RPL; s++) { av[s] = randn(av[s], n[s]); f[s] = n[s]; }
+    for (int s = 0; s < RPL; s++) { av[s] = rsub_subset(av[s], n[s]); f[s] = n[s]; }
 }
 
 template <int NW, int RPL>
@@ -223,14 +238,22 @@ __device__ __forceinline__ int warp_bfs(const Row<NW> (&valid)[RPL], int sx, int
     if (sx == tx && sy == ty) return A_STOP;  // found, empty action list (astar.py:90-92)
     Row<NW> f[RPL], av[RPL], nb[RPL];
 #pragma unroll
-    for (int s = 0; s < RPL; s++) { f[s] = rzero<NW>(); nb[s] = rzero<NW>(); }
+    for (int s = 0; s < RPL; s++) f[s] = rzero<NW>();
     set_bit<NW, RPL>(f, ty, tx, lane);
 #pragma unroll
     for (int s = 0; s < RPL; s++) { f[s] = rand_(f[s], valid[s]); av[s] = randn(valid[s], f[s]); }
-    if (sx + 1 < W) set_bit<NW, RPL>(nb, sy, sx + 1, lane);
-    if (sy + 1 < H) set_bit<NW, RPL>(nb, sy + 1, sx, lane);
-    if (sy - 1 >= 0) set_bit<NW, RPL>(nb, sy - 1, sx, lane);
-    if (sx - 1 >= 0) set_bit<NW, RPL>(nb, sy, sx - 1, lane);
+    {   // the (up to) 4 neighbour cells of the start; columns outside the map are never valid
+        Row<NW> ctr = rzero<NW>();
+#pragma unroll
+        for (int i = 0; i < NW; i++)
+            if (i == (sx >> 6)) ctr.w[i] = 1ull << (sx & 63);
+        const Row<NW> side = ror(rshl1(ctr), rshr1(ctr));
+#pragma unroll
+        for (int s = 0; s < RPL; s++) {
+            const int dr = lane * RPL + s - sy;
+            nb[s] = dr == 0 ? side : ((dr == 1 || dr == -1) ? ctr : rzero<NW>());
+        }
+    }
     const uint32_t m_up = lane != 0 ? 1u : 0u, m_dn = lane != 31 ? 1u : 0u;
     int level = 0;
     for (;;) {
@@ -328,10 +351,11 @@ struct WarpScene {
     uint32_t tick, cursor, n_done;
     int n_created, finished, over;
     uint64_t acted_mask;
+    bool overlap;  // two created AGVs may share a cell (see build_occ)
     // static layout rows + occupancy of created AGVs
     Row<NW> stor[RPL], pick[RPL], inb[RPL], occ[RPL];
 
-    __device__ __forceinline__ WarpScene(const DevCfg &cfg, int lane_) : c(cfg), lane(lane_) {}
+    __device__ __forceinline__ WarpScene(const DevCfg &cfg, int lane_) : c(cfg), lane(lane_), overlap(true) {}
 
     __device__ __forceinline__ void bind(uint8_t *blk_s, uint64_t *vrow, int e) {
         hdr_s = reinterpret_cast<EnvHdr *>(blk_s);
@@ -385,13 +409,20 @@ struct WarpScene {
         __syncwarp();
     }
 
+    // occupancy rows of the created AGVs.  `overlap` is raised when two created AGVs share a
+    // cell: only possible after moves under the A_star protocol with caller-supplied actions
+    // (no AGV-AGV test, Scene.py:159-162) or agv_set_state; while it is false the per-turn
+    // "is another AGV on this cell" ballots reduce to one occupancy-bit test.
     __device__ __forceinline__ void build_occ() {
 #pragma unroll
         for (int s = 0; s < RPL; s++) occ[s] = rzero<NW>();
+        bool dup = false;
         for (int j = 0; j < n_created; j++) {
             const int p = pos_s[j];
+            dup |= test_bit_local<NW, RPL>(occ, (p >> 8) - 1, (p & 255) - 1, lane);
             set_bit<NW, RPL>(occ, (p >> 8) - 1, (p & 255) - 1, lane);
         }
+        overlap = __any_sync(FULL, dup);
     }
 
     __device__ __forceinline__ Agv load_agv(int i) const {
@@ -413,6 +444,10 @@ struct WarpScene {
 
     // any created AGV j != i standing on cell code (x | y<<8)?   (warp ballot)
     __device__ __forceinline__ bool other_at(int i, int cell) const {
+        if (!overlap) {  // occupancy bit, minus AGV i itself
+            if (pos_s[i] == cell) return false;
+            return __any_sync(FULL, test_bit_local<NW, RPL>(occ, (cell >> 8) - 1, (cell & 255) - 1, lane));
+        }
         bool m = false;
         for (int j = lane; j < n_created; j += 32) m |= (j != i) && (pos_s[j] == cell);
         return __any_sync(FULL, m);
@@ -666,6 +701,7 @@ __device__ __forceinline__ void do_turn(WarpScene<NW, RPL> &ws, int i, int proto
         }
     }
     // ---- Explorer.py:145-148: the move is applied iff not is_end
+    if (proto != PROTO_INTELLIGENT && !guided && policy != POLICY_ASTAR) ws.overlap = true;
     if (!end && (dx | dy)) {
         const int oldcell = a.x | (a.y << 8);
         const bool still = ws.other_at(i, oldcell);

@@ -56,7 +56,13 @@ struct StepArgs {
 // ---------------------------------------------------------------- fused tick
 // resident CTAs per SM the register budget is tuned for (ptxas -v: no spills at these bounds)
 template <int NW, int RPL>
-constexpr int tick_min_blocks() { return NW * RPL <= 2 ? 6 : (NW * RPL <= 4 ? 4 : 2); }
+constexpr int tick_min_blocks() {
+#ifdef AGV_TICK_MINB
+    return NW * RPL <= 2 ? AGV_TICK_MINB : (NW * RPL <= 4 ? 4 : 2);
+#else
+    return NW * RPL <= 2 ? 6 : (NW * RPL <= 4 ? 4 : 2);
+#endif
+}
 
 template <int NW, int RPL>
 __global__ void __launch_bounds__(128, tick_min_blocks<NW, RPL>()) k_tick(const DevCfg c, const TickArgs t) {
@@ -352,10 +358,19 @@ static int pick_variant(int H, int W, int *NW, int *RPL) {
 
 static int gcd_i(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
 
-static const int WARPS_PER_CTA = 4;
+static int warps_per_cta() {
+    static int v = 0;
+    if (v == 0) {
+        const char *e = getenv("AGV_WARPS_PER_CTA");  // tuning knob; 1..4
+        v = e ? atoi(e) : 1;  // 1 warp per CTA: a scene frees its SM slot as soon as it is done
+        if (v < 1 || v > 4) v = 1;
+    }
+    return v;
+}
 
 template <typename K, typename... Args>
 static int launch_warps(K kernel, int n_warps, size_t smem_per_warp, cudaStream_t st, Args... args) {
+    const int WARPS_PER_CTA = warps_per_cta();
     const int ctas = (n_warps + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     const size_t smem = smem_per_warp * WARPS_PER_CTA;
     if (smem > 48 * 1024) {

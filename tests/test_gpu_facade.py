@@ -234,7 +234,7 @@ def test_expert_collection_writes_the_reference_csv(pkg, tmp_path):
         assert ex.truncated == 0 and ex.expert_size == m["times"]
         # behavioural cloning from the file: sample -> encode on the GPU -> one Adam step
         import torch
-        net = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(3 * layout.scene_y_width * layout.scene_x_width, 4),
+        net = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(3 * layout.scene_y_width * layout.scene_x_width, 5),  # 5: expert STOPs index 4
                                   torch.nn.Softmax(dim=1)).cuda()
         s, a = ex.sample_data()
         assert len(s) == len(a) and s[0].shape == (3, layout.scene_y_width, layout.scene_x_width)
