@@ -256,6 +256,23 @@ __device__ __forceinline__ int warp_bfs(const Row<NW> (&valid)[RPL], int sx, int
     }
     const uint32_t m_up = lane != 0 ? 1u : 0u, m_dn = lane != 31 ? 1u : 0u;
     int level = 0;
+    // Phase 1: a frontier cell at level L is exactly L steps from the target, and a neighbour
+    // of the start is at least manhattan(start, target) - 1 steps away, so no hit is possible
+    // before that level: expand without the per-level hit test / vote.
+    {
+        const int lmin = abs(sx - tx) + abs(sy - ty) - 1;
+        while (level + 4 <= lmin) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) bfs_expand<NW, RPL>(f, av, m_up, m_dn);
+            level += 4;
+            bool ne = false;
+#pragma unroll
+            for (int s = 0; s < RPL; s++) ne |= rany(f[s]);
+            if (!__any_sync(FULL, ne)) return A_STOP;
+        }
+        while (level < lmin) { bfs_expand<NW, RPL>(f, av, m_up, m_dn); ++level; }
+    }
+    // Phase 2: hit test every level.
     for (;;) {
 #pragma unroll
         for (int u = 0; u < 4; u++) {
