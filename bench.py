@@ -200,6 +200,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scenes", type=int, default=0, help="override scenes per GPU")
     ap.add_argument("--spinup", type=int, default=-1, help="untimed ticks before warm-up (default: 2*AGVs)")
+    ap.add_argument("--mode", default="env", choices=["env", "train"],
+                    help="env: fused tick (headline); train: AG-DQN with the CNN in the loop + replay + learner")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
@@ -259,6 +261,39 @@ def main():
     sc.reset()
     PROTO, POL, OBS = pkg.PROTO_INTELLIGENT, pkg.POLICY_GUIDED, pkg.OBS_CLIP
     out = {}
+
+    if args.mode == "train":
+        # AG-DQN training throughput: sub-step protocol, CNN in the loop,
+        # device replay push + PER sample + DDQN learner step per sub-step
+        M = importlib.import_module(PKG + ".algorithm.MADQN_structure.MADQN")
+        agent = M.BatchedAgent(sc, memory_size=1 << 20, batch_size=256, epsilon=0.8, ddp=world > 1)
+        for _ in range(max(warmup, 2 * N)):
+            agent.tick(train=True)
+        du = importlib.import_module(PKG + ".dist_util")
+        sc.counters()
+        l0 = lib.agv_launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        du.barrier(dev)
+        ev0.record()
+        for _ in range(steps):
+            agent.tick(train=True)
+        ev1.record()
+        du.barrier(dev)
+        ms, turns = du.reduce_timing(ev0.elapsed_time(ev1), sc.counters()[0], dev)
+        if rank == 0:
+            print(json.dumps({
+                "metric": METRIC, "value": turns / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+                "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16 autocast CNN, u64 bitboards", "data": "synthetic",
+                "config": {"workload": "AG-DQN training: " + desc, "mode": "train", "agvs_per_scene": N,
+                           "scenes_per_gpu": E, "learner": "1 DDQN step (batch 256) per sub-step, PER on device",
+                           "epsilon": 0.8},
+                "gpu_launches": int(lib.agv_launch_count() - l0), "learner_updates": agent.learn_step_counter,
+                "turns_per_step": turns / steps}))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
 
     def step():
         sc.tick(PROTO, POL, OBS, want_lens=False, out=out)

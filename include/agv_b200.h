@@ -137,9 +137,11 @@ int agv_encode(AgvHandle *h, int32_t k, int32_t obs_kind, int32_t post, void *ou
 int agv_bfs_action(AgvHandle *h, int32_t k, int32_t matrix, int8_t *action_dev, uint16_t *pathlen_dev,
                    void *stream);
 /* Explorer.execute_action + Scene.py:155-158 for AGV k with action_dev int8[E]
- * (negative = GUIDED fallback).  acted_dev uint8[E] = 1 where the turn happened. */
+ * (negative = GUIDED fallback).  acted_dev uint8[E] = 1 where the turn happened;
+ * act_out_dev int8[E] (optional) = the action executed (the BFS action for a fallback),
+ * AGV_NO_TURN where no turn happened. */
 int agv_step_turn(AgvHandle *h, int32_t k, int32_t proto, const int8_t *action_dev, float *reward_dev,
-                  uint8_t *done_dev, uint8_t *acted_dev, uint16_t *slen_dev, void *stream);
+                  uint8_t *done_dev, uint8_t *acted_dev, uint16_t *slen_dev, int8_t *act_out_dev, void *stream);
 int agv_end_tick(AgvHandle *h, void *stream);    /* Scene.check_new_veh */
 
 /* ---- state access (parity dumps, Scene.create_info Scene.py:341-352) ---------

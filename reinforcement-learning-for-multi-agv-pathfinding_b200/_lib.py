@@ -37,7 +37,7 @@ SYMBOLS = {
     "agv_begin_tick": (C.c_int, [_vp, _vp]),
     "agv_encode": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "agv_bfs_action": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp]),
-    "agv_step_turn": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "agv_step_turn": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "agv_end_tick": (C.c_int, [_vp, _vp]),
     "agv_get_state": (C.c_int, [_vp, _vp, _vp, _vp]),
     "agv_set_state": (C.c_int, [_vp, _vp, _vp, _vp]),

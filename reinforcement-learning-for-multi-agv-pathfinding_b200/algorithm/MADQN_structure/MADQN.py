@@ -1,0 +1,179 @@
+"""Batched AG-DQN (DDQN with A*-guided exploration) driving thousands of scenes at once.
+
+Reference: src/algorithm/MADQN_structure/MADQN.py:13-200 and Controller.py:21-145 (one AGV
+decision, one stored transition and one optimiser step at a time).  The arithmetic of the
+agent is unchanged -- same 6-conv CNN on the 3x7x7 limited-visual state (Net, MADQN.py:13-51),
+epsilon = probability of using the network, otherwise the A* guidance action
+(choose_action, 96-111), priority (|TD error| + 0.01)^0.6 set at insert (store_transition,
+113-132; PER.py:79-80), DDQN target + SmoothL1 + Adagrad(lr 0.01), target sync every 100
+updates (update_network, 134-171) -- but every tensor has a leading scene dimension and the
+environment side is the CUDA path:
+
+    agv_begin_tick
+    for k in AGVs:   obs  = agv_encode(k)                      # create_state, bf16 [E,3,7,7]
+                     a    = u < eps ? argmax Q(obs) : -1       # -1 = "A* guidance" ...
+                     r, done = agv_step_turn(k, a)             # ... resolved inside the kernel
+                     obs' = agv_encode(k, post=1)
+                     agv_replay_push(obs, a, r, obs', done, priority)
+                     learner step(s) on agv_replay_sample
+    agv_end_tick
+
+The CNN is the only dense contraction and stays in PyTorch (bf16 autocast, tensor cores).
+Multi-GPU: scenes and replay shard per rank; DistributedDataParallel all-reduces the gradients
+over NCCL.  Known reference defect kept out of the data: a guidance STOP (action 4) cannot
+index the 4-wide Q row (IndexError in MADQN.py:118), so STOP transitions are not stored.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ... import _lib as L
+from ...replay import DeviceReplay
+
+
+class Net(nn.Module):
+    """MADQN.py:13-51: conv 3->64->64->128->128->256->256 (3x3, pad 1, ReLU), one 2x2 max-pool
+    (only conv_pool3 is applied in forward), fc 2304->256->actions."""
+
+    def __init__(self, num_inputs=3, num_actions=4, map_xdim=7, map_ydim=7):
+        super().__init__()
+        self.conv1 = nn.Conv2d(num_inputs, 64, 3, 1, 1)
+        self.conv2 = nn.Conv2d(64, 64, 3, 1, 1)
+        self.conv_pool1 = nn.MaxPool2d(2, 2)
+        self.conv3 = nn.Conv2d(64, 128, 3, 1, 1)
+        self.conv4 = nn.Conv2d(128, 128, 3, 1, 1)
+        self.conv_pool2 = nn.MaxPool2d(2, 2)
+        self.conv5 = nn.Conv2d(128, 256, 3, 1, 1)
+        self.conv6 = nn.Conv2d(256, 256, 3, 1, 1)
+        self.conv_pool3 = nn.MaxPool2d(2, 2)
+        self.fc3 = nn.Linear(2304, 256)
+        self.fc4 = nn.Linear(256, num_actions)
+
+    def forward(self, x):
+        x = F.relu(self.conv1(x))
+        x = F.relu(self.conv2(x))
+        x = F.relu(self.conv3(x))
+        x = F.relu(self.conv4(x))
+        x = F.relu(self.conv5(x))
+        x = F.relu(self.conv6(x))
+        x = self.conv_pool3(x)
+        x = F.relu(self.fc3(x.reshape(x.size(0), -1)))
+        return self.fc4(x)
+
+
+class BatchedAgent:
+    def __init__(self, scene, policy_net=None, target_net=None, memory_size=1 << 20, batch_size=256,
+                 start_training_info_number=100, gamma=0.95, lr=0.01, target_replace_iter=100, epsilon=0.8,
+                 updates_per_substep=1, autocast=True, ddp=False, seed=0):
+        self.scene = scene
+        self.device = scene.device
+        self.policy_network = (policy_net or Net()).to(self.device).to(memory_format=torch.channels_last)
+        self.target_network = (target_net or Net()).to(self.device).to(memory_format=torch.channels_last)
+        self.target_network.load_state_dict(self.policy_network.state_dict())
+        self._train_net = self.policy_network
+        if ddp:
+            from torch.nn.parallel import DistributedDataParallel
+            self._train_net = DistributedDataParallel(self.policy_network, device_ids=[scene.device_index])
+        self.epsilon_start = self.epsilon = epsilon
+        self.epsilon_end, self.epsilon_count = 1.0, 0
+        self.memory_size, self.batch_size = memory_size, batch_size
+        self.start_training_info_number = start_training_info_number
+        self.learn_step_counter = 0
+        self.TARGET_REPLACE_ITER = target_replace_iter
+        self.GAMMA = gamma
+        self.updates_per_substep = updates_per_substep
+        self.memory = DeviceReplay(memory_size, (3, scene.K, scene.K), device=scene.device_index)
+        self.optim = torch.optim.Adagrad(self.policy_network.parameters(), lr)
+        self.loss_function = nn.SmoothL1Loss()
+        self.autocast = autocast
+        self.gen = torch.Generator(device=self.device)
+        self.gen.manual_seed(seed)
+        self.loss_value = []
+        self.stored = 0
+        self.reward_acc = torch.zeros((), dtype=torch.float64, device=self.device)
+
+    # ------------------------------------------------------------------ acting
+    def q_values(self, net, obs):
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.autocast):
+            return net(obs.contiguous(memory_format=torch.channels_last)).float()
+
+    def tick(self, train=True, epsilon=None, u=None):
+        """one Scene.run_mode pass of every scene with the network in the loop; returns the
+        number of AGV turns taken.  `u` (optional [N, E] uniforms) injects the epsilon draws."""
+        sc = self.scene
+        eps = self.epsilon if epsilon is None else epsilon
+        turns = torch.zeros((), dtype=torch.int64, device=self.device)
+        sc.begin_tick()
+        for k in range(sc.N):
+            obs, will = sc.encode(k, L.OBS_CLIP)
+            with torch.no_grad():
+                q = self.q_values(self.policy_network, obs)
+            a_nn = q.argmax(1).to(torch.int8)
+            uk = torch.rand(sc.E, device=self.device, generator=self.gen) if u is None else u[k]
+            a_in = torch.where(uk < eps, a_nn, torch.full_like(a_nn, -1))
+            rew, done, acted, _ = sc.step_turn(k, L.PROTO_INTELLIGENT, a_in)
+            a_exec = sc.last_action
+            turns += acted.sum()
+            self.reward_acc += rew.double().sum()
+            if not train:
+                continue
+            nobs, _ = sc.encode(k, L.OBS_CLIP, post=True)
+            with torch.no_grad():
+                qn = self.q_values(self.policy_network, nobs)
+                # store_transition, MADQN.py:113-128
+                storable = (acted > 0) & (a_exec >= 0) & (a_exec < q.shape[1])
+                idx = a_exec.clamp(0, q.shape[1] - 1).long().unsqueeze(1)
+                old_val = q.gather(1, idx).squeeze(1)
+                new_val = rew + self.GAMMA * qn.max(1)[0] * (done == 0)
+                prio = ((old_val - new_val).abs().double() + 0.01) ** 0.6
+                act_store = torch.where(storable, a_exec, torch.full_like(a_exec, -1))
+            self.memory.push(act_store.contiguous(), rew.contiguous(), done.contiguous(), obs.contiguous(),
+                             nobs.contiguous(), prio.contiguous())
+            self.stored += 1
+            if self.stored * sc.E >= self.start_training_info_number:
+                for _ in range(self.updates_per_substep):
+                    self.update_network()
+        sc.end_tick()
+        return turns
+
+    # ------------------------------------------------------------------ learning
+    def update_network(self):
+        """MADQN.py:134-171 on a device-sampled batch"""
+        if self.learn_step_counter % self.TARGET_REPLACE_ITER == 0:
+            self.target_network.load_state_dict(self.policy_network.state_dict())
+        self.learn_step_counter += 1
+        u = torch.rand(self.batch_size, dtype=torch.float64, device=self.device, generator=self.gen)
+        b = self.memory.sample(self.batch_size, u)
+        batch_s, batch_n = b["obs"], b["next_obs"]
+        batch_a = b["act"].long().clamp(min=0).unsqueeze(1)
+        batch_r = b["reward"].unsqueeze(1)
+        not_done = (b["done"] == 0).float().unsqueeze(1)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.autocast):
+            state_action_values = self._train_net(batch_s.contiguous(memory_format=torch.channels_last)).float() \
+                .gather(1, batch_a)
+            with torch.no_grad():
+                nt = self.target_network(batch_n.contiguous(memory_format=torch.channels_last)).float()
+                npol = self.policy_network(batch_n.contiguous(memory_format=torch.channels_last)).float()
+                next_state_values = nt.gather(1, npol.argmax(1, keepdim=True))
+                expected = next_state_values * self.GAMMA * not_done + batch_r
+        loss = self.loss_function(state_action_values, expected)
+        self.optim.zero_grad(set_to_none=True)
+        loss.backward()
+        self.optim.step()
+        self.loss_value.append(loss.detach())
+        return loss
+
+    def change_explore_rate(self, times):
+        """MADQN.py:182-190"""
+        if self.epsilon_count >= times:
+            self.epsilon = self.epsilon_end
+        else:
+            self.epsilon = self.epsilon + (self.epsilon_end - self.epsilon_start) / times
+        self.epsilon_count += 1
+
+    def save(self, path_policy, path_target):
+        """whole-module pickles like Controller.py:161-172 (policy_net.pt / target_net.pt)"""
+        torch.save(self.policy_network, path_policy)
+        torch.save(self.target_network, path_target)

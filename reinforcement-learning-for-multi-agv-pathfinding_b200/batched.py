@@ -176,8 +176,9 @@ class BatchedScene:
         done = self._get("st_done", (self.E,), torch.uint8)
         acted = self._get("st_acted", (self.E,), torch.uint8)
         slen = self._get("st_slen", (self.E,), torch.int16)
+        self.last_action = self._get("st_act", (self.E,), torch.int8)  # action executed (BFS action for -1)
         L.check(self.lib.agv_step_turn(self._h, k, proto, _ptr(a), _ptr(rew), _ptr(done), _ptr(acted), _ptr(slen),
-                                       self._stream()), "agv_step_turn")
+                                       _ptr(self.last_action), self._stream()), "agv_step_turn")
         return rew, done, acted, slen
 
     # ------------------------------------------------------------------ state access

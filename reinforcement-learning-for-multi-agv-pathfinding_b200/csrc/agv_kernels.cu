@@ -607,13 +607,13 @@ int agv_bfs_action(AgvHandle *h, int32_t k, int32_t matrix, int8_t *action_dev, 
 }
 
 int agv_step_turn(AgvHandle *h, int32_t k, int32_t proto, const int8_t *action_dev, float *reward_dev,
-                  uint8_t *done_dev, uint8_t *acted_dev, uint16_t *slen_dev, void *stream) {
+                  uint8_t *done_dev, uint8_t *acted_dev, uint16_t *slen_dev, int8_t *act_out_dev, void *stream) {
     if (!h || k < 0 || k >= h->cfg.N || proto < 0 || proto > 1) return AGV_E_INVALID;
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     StepArgs s; memset(&s, 0, sizeof(s));
     plan_step(h, s, 0);
     s.k = k; s.proto = proto; s.action = action_dev; s.reward = reward_dev; s.done = done_dev; s.acted = acted_dev;
-    s.slen = slen_dev;
+    s.slen = slen_dev; s.action_out = act_out_dev;
 #define CALL(NW_, RPL_) return launch_warps(k_step_turn<NW_, RPL_>, h->cfg.E, s.per_warp, (cudaStream_t)stream, h->dc, s)
     DISPATCH(h, CALL);
 #undef CALL

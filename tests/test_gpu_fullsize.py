@@ -1,0 +1,82 @@
+"""BASELINE-size runs (configs[2] 64x64 / 64 AGVs / 16384 scenes, configs[4] 128x128) checked
+through size-independent properties + exact oracle parity on a scattered sample of scenes."""
+import numpy as np
+import pytest
+
+import bench
+from conftest import load_pkg
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _invariants(grid, hdr, agv, T):
+    H, W = grid.shape
+    nc = hdr[:, 4]
+    N = agv.shape[1]
+    created = np.arange(N)[None, :] < nc[:, None]
+    x, y, tx, ty = agv[..., 0], agv[..., 1], agv[..., 2], agv[..., 3]
+    assert (x >= 1).all() and (x <= W).all() and (y >= 1).all() and (y <= H).all()
+    assert (hdr[:, 1] <= T).all() and (hdr[:, 2] <= hdr[:, 1]).all()  # n_done <= cursor <= T
+    # intelligent protocol: no two created AGVs ever share a cell
+    cell = (y.astype(np.int64) * 256 + x) * created + (-1 - np.arange(N))[None, :] * (~created)
+    s = np.sort(cell, axis=1)
+    assert (s[:, 1:] != s[:, :-1]).all()
+    # a loaded AGV is never on a picking station or storage station other than its own task's cells
+    code = grid[y - 1, x - 1]
+    loaded = agv[..., 5].astype(bool) & created
+    on_station = loaded & (code != 0)
+    # loaded on a storage cell happens only right after lifting (stage 1: the task's storage cell)
+    # or on its way back onto the target (stage 2 target); on a picking cell only at the target /
+    # right after delivery (stage 2 starts on the picking station)
+    stage = agv[..., 4]
+    at_target = (x == tx) & (y == ty)
+    ok = at_target | ((code == 1) & (stage == 1)) | ((code == 2) & (stage == 2))
+    assert (ok | ~on_station).all()
+    # uncreated AGVs are parked at (1,1) with stage 0
+    assert ((x == 1) & (y == 1) & (stage == 0))[~created].all()
+
+
+@pytest.mark.parametrize("workload,E,ticks", [("c3", 16384, 90), ("c5", 2048, 80)])
+def test_fullsize_properties_and_sampled_parity(workload, E, ticks):
+    import torch
+    pkg = load_pkg()
+    gridf, N, _, _ = bench.WORKLOADS[workload]
+    grid = gridf()
+    tasks = bench.synth_tasks(grid, E, seed=7)
+    T = tasks.shape[1]
+    sample = sorted(set(int(v) for v in np.linspace(0, E - 1, 6)))
+    envs = {e: orc.Env(grid, tasks[e], N) for e in sample}
+    checks = []
+    for rep in range(2):
+        sc = pkg.BatchedScene(grid, E, N, tasks=tasks, P=3, auto_reset=True)
+        sc.reset()
+        cs = torch.zeros((), dtype=torch.int64, device=sc.device)
+        turns = 0
+        for t in range(ticks):
+            out = sc.tick(pkg.PROTO_INTELLIGENT, pkg.POLICY_GUIDED, pkg.OBS_CLIP)
+            act = out["act"]
+            cs = cs * 1000003 + (act.long() + 2).sum() * 31 + out["obs"].float().sum().long() \
+                + (out["reward"] * 4).long().sum() + out["done"].long().sum() * 7
+            turns += int((act >= 0).sum())
+            if rep == 0 and (t % 15 == 14 or t == ticks - 1):
+                hdr, agv = sc.get_state()
+                _invariants(grid, hdr, agv, T)
+            if rep == 0:
+                a_np = act[sample].cpu().numpy()
+                r_np = out["reward"][sample].cpu().numpy()
+                d_np = out["done"][sample].cpu().numpy()
+                o_np = out["obs"][sample].float().cpu().numpy()
+                for q, e in enumerate(sample):
+                    env = envs[e]
+                    if env.state()[0][5]:
+                        env.reset()
+                    n, a, r, d, pl, sl, ob, _ = env.tick_obs(orc.PROTO_INTELLIGENT, orc.POLICY_GUIDED, obs_kind=1, P=3)
+                    assert np.array_equal(a_np[q], a) and np.array_equal(r_np[q], r.astype(np.float32))
+                    assert np.array_equal(d_np[q], d) and np.array_equal(o_np[q], ob)
+        c_turns = sc.counters()[0]
+        assert c_turns == turns  # the throughput counter counts exactly the turns taken
+        checks.append((int(cs), turns))
+        sc.close()
+    assert checks[0] == checks[1]  # bitwise deterministic
+    assert checks[0][1] > E * ticks // 4
