@@ -202,6 +202,11 @@ def main():
     ap.add_argument("--spinup", type=int, default=-1, help="untimed ticks before warm-up (default: 2*AGVs)")
     ap.add_argument("--mode", default="env", choices=["env", "train"],
                     help="env: fused tick (headline); train: AG-DQN with the CNN in the loop + replay + learner")
+    ap.add_argument("--obs", default="clip", choices=["clip", "full"],
+                    help="clip: limited visual 3x7x7 (AG-DQN, headline); full: 3xHxW (PG/AC/DQN controllers)")
+    ap.add_argument("--policy", default="guided", choices=["guided", "astar"],
+                    help="guided: intelligent protocol + A* guidance on matrix b (headline); "
+                         "astar: Scene A_star control mode (matrix a, no episode end)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
@@ -260,6 +265,10 @@ def main():
     del tasks
     sc.reset()
     PROTO, POL, OBS = pkg.PROTO_INTELLIGENT, pkg.POLICY_GUIDED, pkg.OBS_CLIP
+    if args.policy == "astar":
+        PROTO, POL = pkg.PROTO_ASTAR, pkg.POLICY_ASTAR
+    if args.obs == "full":
+        OBS = pkg.OBS_FULL
     out = {}
 
     if args.mode == "train":
@@ -341,7 +350,10 @@ def main():
     act_host = torch.full((E, N), -1, dtype=torch.int8).pin_memory()
 
     def step_e2e():
-        sc.tick_host(PROTO, pkg.POLICY_GIVEN, OBS, actions_host=act_host)
+        if args.policy == "guided":
+            sc.tick_host(PROTO, pkg.POLICY_GIVEN, OBS, actions_host=act_host)
+        else:
+            sc.tick_host(PROTO, POL, OBS)
 
     for _ in range(3):
         step_e2e()
@@ -359,7 +371,8 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     K = 7
-    unit_compulsory = 3 * K * K * 2 + 32 + 1 + 4 + 1        # 332 B per AGV-step
+    obs_bytes = 3 * K * K * 2 if args.obs == "clip" else 3 * H * W * 2
+    unit_compulsory = obs_bytes + 32 + 1 + 4 + 1            # 332 B per AGV-step (clip)
     unit_bfs = 2 * H * W                                    # one materialised uint16 field
     per_launch_units = turns / max(1, steps) / world
     dur_s = ms * 1e-3 / steps
@@ -379,10 +392,14 @@ def main():
             "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/u64 bitboards, bf16 obs", "data": "synthetic",
             "config": {"workload": desc, "H": H, "W": W, "agvs_per_scene": N, "scenes_per_gpu": E,
-                       "tasks_per_scene": int((grid == 1).sum()), "protocol": "intelligent + A* guidance (matrix b)",
-                       "obs": "clip 3x7x7 bf16", "spinup_ticks": spin,
-                       "l2": "outputs larger than L2: %.0f MB obs written per step" % (E * N * 294 / 1e6)},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * N * world,
+                       "tasks_per_scene": int((grid == 1).sum()),
+                       "protocol": ("intelligent + A* guidance (matrix b)" if args.policy == "guided"
+                                    else "A_star control mode (matrix a)"),
+                       "obs": "clip 3x7x7 bf16" if args.obs == "clip" else "full 3x%dx%d bf16" % (H, W),
+                       "spinup_ticks": spin,
+                       "l2": "outputs larger than L2: %.0f MB obs written per step" % (E * N * obs_bytes / 1e6)},
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": (E * N * world) if args.policy == "guided" else 0,
                     "d2h_bytes_per_step": E * N * 6 * world, "ms_per_step": ms_e / steps},
             "gpu_launches": int(launches),
             "clocks": clk,

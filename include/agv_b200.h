@@ -110,7 +110,8 @@ int agv_reset(AgvHandle *h, const uint8_t *env_mask_dev, void *stream);
  *   plen_dev     uint16[E,N]  len(action_list) of the policy BFS (0 = STOP/none)
  *   slen_dev     uint16[E,N]  rectify_reward's path_length_new (Explorer.py:220),
  *                             0xFFFF when the shaped branch was not taken
- *   obs_dev / next_obs_dev  bf16 [E,N,3,K,K] or [E,N,3,H,W] (zeros for no turn) */
+ *   obs_dev / next_obs_dev  bf16 [E,N,3,K,K] or [E,N,3,H,W]; records of AGVs that took no
+ *                             turn are NOT written (mask with act_out >= 0) */
 int agv_tick(AgvHandle *h, int32_t proto, int32_t policy, int32_t obs_kind,
              const int8_t *action_dev, int8_t *act_out_dev, float *reward_dev, uint8_t *done_dev,
              uint16_t *plen_dev, uint16_t *slen_dev, void *obs_dev, void *next_obs_dev, void *stream);

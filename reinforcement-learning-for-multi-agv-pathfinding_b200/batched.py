@@ -76,7 +76,8 @@ class BatchedScene:
     def _get(self, name, shape, dtype):
         b = self._buf.get(name)
         if b is None or tuple(b.shape) != tuple(shape) or b.dtype != dtype:
-            b = torch.empty(shape, dtype=dtype, device=self.device)
+            # zero-initialised once: observation records of AGVs without a turn are never written
+            b = torch.zeros(shape, dtype=dtype, device=self.device)
             self._buf[name] = b
         return b
 

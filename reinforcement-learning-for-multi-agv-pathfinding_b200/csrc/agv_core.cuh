@@ -369,10 +369,19 @@ struct WarpScene {
     int n_created, finished, over;
     uint64_t acted_mask;
     bool overlap;  // two created AGVs may share a cell (see build_occ)
+    uint32_t cnt_turns, cnt_ended, cnt_bad;  // statistics, flushed once per kernel (flush_counters)
     // static layout rows + occupancy of created AGVs
     Row<NW> stor[RPL], pick[RPL], inb[RPL], occ[RPL];
 
-    __device__ __forceinline__ WarpScene(const DevCfg &cfg, int lane_) : c(cfg), lane(lane_), overlap(true) {}
+    __device__ __forceinline__ WarpScene(const DevCfg &cfg, int lane_) : c(cfg), lane(lane_), overlap(true), cnt_turns(0), cnt_ended(0), cnt_bad(0) {}
+
+    __device__ __forceinline__ void flush_counters() {
+        if (lane == 0) {
+            if (cnt_turns) atomicAdd(c.counters + 0, (unsigned long long)cnt_turns);
+            if (cnt_ended) atomicAdd(c.counters + 1, (unsigned long long)cnt_ended);
+            if (cnt_bad) atomicAdd(c.counters + 2, (unsigned long long)cnt_bad);
+        }
+    }
 
     __device__ __forceinline__ void bind(uint8_t *blk_s, uint64_t *vrow, int e) {
         hdr_s = reinterpret_cast<EnvHdr *>(blk_s);
@@ -418,11 +427,9 @@ struct WarpScene {
         acted_mask = hdr_s->acted_mask;
     }
     __device__ __forceinline__ void regs_to_hdr() {
-        if (lane == 0) {
-            hdr_s->tick = tick; hdr_s->cursor = cursor; hdr_s->n_done = n_done;
-            hdr_s->n_created = (uint16_t)n_created; hdr_s->finished = (uint8_t)finished;
-            hdr_s->over = (uint8_t)over; hdr_s->acted_mask = acted_mask;
-        }
+        hdr_s->tick = tick; hdr_s->cursor = cursor; hdr_s->n_done = n_done;
+        hdr_s->n_created = (uint16_t)n_created; hdr_s->finished = (uint8_t)finished;
+        hdr_s->over = (uint8_t)over; hdr_s->acted_mask = acted_mask;
         __syncwarp();
     }
 
@@ -449,13 +456,13 @@ struct WarpScene {
         a.stage = m & 3; a.loaded = (m >> 2) & 1; a.idle = (m >> 3) & 1; a.order = ord_s[i];
         return a;
     }
+    // every lane stores the same (warp-uniform) values: one wavefront per store and no
+    // divergent `if (lane == 0)` block (BSSY/BSYNC pairs were top stall_no_instruction sites)
     __device__ __forceinline__ void store_agv(int i, const Agv &a) {
-        if (lane == 0) {
-            pos_s[i] = (uint16_t)(a.x | (a.y << 8));
-            tgt_s[i] = (uint16_t)(a.tx | (a.ty << 8));
-            ord_s[i] = (uint16_t)a.order;
-            meta_s[i] = (uint8_t)meta_pack(a);
-        }
+        pos_s[i] = (uint16_t)(a.x | (a.y << 8));
+        tgt_s[i] = (uint16_t)(a.tx | (a.ty << 8));
+        ord_s[i] = (uint16_t)a.order;
+        meta_s[i] = (uint8_t)meta_pack(a);
         __syncwarp();
     }
 
@@ -595,29 +602,44 @@ struct WarpScene {
         if (c.K == 7) encode_clip_impl<7>(dst, a);
         else encode_clip_impl<0>(dst, a);
     }
-    // StateManager.create_state(obs_clip=False) straight to a [3,H,W] bf16 record in HBM
+    // StateManager.create_state(obs_clip=False) straight to a [3,H,W] bf16 record in HBM.
+    // W % 8 == 0: one 16-byte store = 8 cells of one row; the two one-hot planes are zero
+    // vectors except one; the valid plane expands 8 mask bits with two-bits-per-IMAD
+    // (t = b0 | b1 << 16; t * 0x3F80 = {bf16(b0), bf16(b1)}).
     __device__ __forceinline__ void encode_full(uint16_t *dst, const Agv &a) const {
         const int H = c.H, W = c.W, HW = H * W, n = 3 * HW;
         const int cpos = (a.y - 1) * W + (a.x - 1), tpos = (a.ty - 1) * W + (a.tx - 1);
         if ((W & 7) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-            // 8 consecutive columns of one row of one channel per 16-byte store
-            const int nv = n >> 3;
-            for (int v8 = lane; v8 < nv; v8 += 32) {
-                const int flat = v8 << 3;
-                const int ch = flat / HW, p = flat - ch * HW;
-                unsigned bits;
-                if (ch == 0) bits = (cpos >= p && cpos < p + 8) ? (1u << (cpos - p)) : 0u;
-                else if (ch == 1) bits = (tpos >= p && tpos < p + 8) ? (1u << (tpos - p)) : 0u;
-                else {
-                    const int r = p / W, cc = p - r * W;
-                    bits = (unsigned)((vrow_s[r * NW + (cc >> 6)] >> (cc & 63)) & 0xffull);
+            const int nvr = W >> 3, nvc = H * nvr;
+            uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+            const int cv = cpos >> 3, tv = tpos >> 3;
+            for (int v = lane; v < nvc; v += 32) {
+                uint4 o0 = make_uint4(0, 0, 0, 0), o1 = make_uint4(0, 0, 0, 0);
+                if (v == cv) {
+                    const unsigned val = (unsigned)BF16_ONE << ((cpos & 1) * 16), w = (cpos & 7) >> 1;
+                    o0.x = w == 0 ? val : 0u; o0.y = w == 1 ? val : 0u; o0.z = w == 2 ? val : 0u; o0.w = w == 3 ? val : 0u;
                 }
+                if (v == tv) {
+                    const unsigned val = (unsigned)BF16_ONE << ((tpos & 1) * 16), w = (tpos & 7) >> 1;
+                    o1.x = w == 0 ? val : 0u; o1.y = w == 1 ? val : 0u; o1.z = w == 2 ? val : 0u; o1.w = w == 3 ? val : 0u;
+                }
+                d4[v] = o0;
+                d4[nvc + v] = o1;
+            }
+            int r = lane / nvr, c8 = lane - r * nvr;
+            const int dr = 32 / nvr, dc = 32 - dr * nvr;
+            uint4 *d2 = d4 + 2 * nvc;
+            for (int v = lane; v < nvc; v += 32) {
+                const unsigned bits = (unsigned)(vrow_s[r * NW + (c8 >> 3)] >> ((c8 & 7) * 8)) & 0xffu;
                 uint4 o;
-                o.x = ((bits & 1u) ? (unsigned)BF16_ONE : 0u) | ((bits & 2u) ? ((unsigned)BF16_ONE << 16) : 0u);
-                o.y = ((bits & 4u) ? (unsigned)BF16_ONE : 0u) | ((bits & 8u) ? ((unsigned)BF16_ONE << 16) : 0u);
-                o.z = ((bits & 16u) ? (unsigned)BF16_ONE : 0u) | ((bits & 32u) ? ((unsigned)BF16_ONE << 16) : 0u);
-                o.w = ((bits & 64u) ? (unsigned)BF16_ONE : 0u) | ((bits & 128u) ? ((unsigned)BF16_ONE << 16) : 0u);
-                reinterpret_cast<uint4 *>(dst)[v8] = o;
+                unsigned u, t;
+                u = bits & 3u;        t = (u | (u << 15)) & 0x10001u; o.x = t * (unsigned)BF16_ONE;
+                u = (bits >> 2) & 3u; t = (u | (u << 15)) & 0x10001u; o.y = t * (unsigned)BF16_ONE;
+                u = (bits >> 4) & 3u; t = (u | (u << 15)) & 0x10001u; o.z = t * (unsigned)BF16_ONE;
+                u = (bits >> 6) & 3u; t = (u | (u << 15)) & 0x10001u; o.w = t * (unsigned)BF16_ONE;
+                d2[v] = o;
+                c8 += dc; r += dr;
+                if (c8 >= nvr) { c8 -= nvr; r++; }
             }
         } else {
             for (int idx = lane; idx < n; idx += 32) {
@@ -662,33 +684,32 @@ struct TurnOut {
 // -> Scene.py:155 correction -> [encode next_obs].  Warp-uniform control flow.
 // obs_dst / next_dst: destination record (shared staging for OBS_CLIP, global for
 // OBS_FULL) or nullptr.
-template <int NW, int RPL>
+// OBS (observation kind) and SHAPED (settings.Sparse_Reward) are compile-time so that each
+// kernel carries only the code of its own path: the turn body is re-fetched by every warp
+// once per turn and instruction-fetch stalls were the top stall reason with one fat kernel.
+template <int NW, int RPL, int OBS, bool SHAPED>
 __device__ __forceinline__ void do_turn(WarpScene<NW, RPL> &ws, int i, int proto, int policy, int given,
-                                        int obs_kind, uint16_t *obs_dst, uint16_t *next_dst, TurnOut &out) {
+                                        uint16_t *obs_dst, uint16_t *next_dst, TurnOut &out) {
     const DevCfg &c = ws.c;
     const int lane = ws.lane;
     Agv a = ws.load_agv(i);
     Row<NW> v[RPL];
-    const bool want_obs = (obs_kind != OBS_NONE) && (obs_dst != nullptr);
+    const bool want_obs = (OBS != OBS_NONE) && (obs_dst != nullptr);
     const bool guided = (policy == POLICY_GUIDED) || (policy == POLICY_GIVEN && given < 0);
     if (want_obs || guided) ws.valid_b(a, i, v);
-    if (want_obs) {
+    if (OBS != OBS_NONE && want_obs) {
         ws.rows_to_smem(v);
-        if (obs_kind == OBS_CLIP) ws.encode_clip(obs_dst, a);
+        if (OBS == OBS_CLIP) ws.encode_clip(obs_dst, a);
         else ws.encode_full(obs_dst, a);
     }
-    int action, plen = 0;
-    if (guided) {
+    int action = given, plen = 0;
+    const bool policy_bfs = guided || policy == POLICY_ASTAR;
+    if (!guided && policy == POLICY_ASTAR) ws.valid_a(a, v);
+    if (policy_bfs) {  // the one policy-search call site (matrix a or b is already in v)
         action = warp_bfs<NW, RPL>(v, a.x - 1, a.y - 1, a.tx - 1, a.ty - 1, c.H, c.W, lane, plen);
-    } else if (policy == POLICY_ASTAR) {
-        ws.valid_a(a, v);
-        action = warp_bfs<NW, RPL>(v, a.x - 1, a.y - 1, a.tx - 1, a.ty - 1, c.H, c.W, lane, plen);
-    } else {
-        action = given;
-        if (action > A_STOP) {  // the reference raises KeyError (utils.py:21); counted, treated as STOP
-            if (lane == 0) atomicAdd(c.counters + 2, 1ull);
-            action = A_STOP;
-        }
+    } else if (action > A_STOP) {  // the reference raises KeyError (utils.py:21); counted, treated as STOP
+        ws.cnt_bad++;
+        action = A_STOP;
     }
     // ---- Explorer.check_action, Explorer.py:151-208
     const int dx = (action == A_RIGHT) - (action == A_LEFT);
@@ -706,7 +727,7 @@ __device__ __forceinline__ void do_turn(WarpScene<NW, RPL> &ws, int i, int proto
         else if (code == 2 && !at_target) { r = -1; end = 1; }
         else if (proto == PROTO_INTELLIGENT && ws.other_at(i, nx | (ny << 8))) { r = -1; end = 1; }
         else if (at_target) { r = 1; ws.continue_working(a); }
-        else if (c.shaped) {
+        else if (SHAPED) {
             // Explorer.rectify_reward (Explorer.py:210-249): only path_length_new matters
             ws.valid_a(a, v);
             int l = 0;
@@ -734,15 +755,13 @@ __device__ __forceinline__ void do_turn(WarpScene<NW, RPL> &ws, int i, int proto
         end = 0;  // is_end is ignored by the loop in A_star / manual mode (Scene.py:159-162)
     }
     ws.acted_mask |= (1ull << i);
-    if (lane == 0) {
-        atomicAdd(c.counters + 0, 1ull);
-        if (end) atomicAdd(c.counters + 1, 1ull);
-    }
-    if (next_dst != nullptr && obs_kind != OBS_NONE) {
+    ws.cnt_turns++;
+    ws.cnt_ended += end;
+    if (OBS != OBS_NONE && next_dst != nullptr) {
         // store_info's create_state on the snapshot after the move (Scene.py:156)
         ws.valid_b(a, i, v);
         ws.rows_to_smem(v);
-        if (obs_kind == OBS_CLIP) ws.encode_clip(next_dst, a);
+        if (OBS == OBS_CLIP) ws.encode_clip(next_dst, a);
         else ws.encode_full(next_dst, a);
     }
     out.action = action;

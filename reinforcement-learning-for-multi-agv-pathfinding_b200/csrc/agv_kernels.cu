@@ -64,7 +64,7 @@ constexpr int tick_min_blocks() {
 #endif
 }
 
-template <int NW, int RPL>
+template <int NW, int RPL, int OBS, bool SHAPED>
 __global__ void __launch_bounds__(128, tick_min_blocks<NW, RPL>()) k_tick(const DevCfg c, const TickArgs t) {
     WARP_PROLOGUE(t)
     int8_t *o_act = reinterpret_cast<int8_t *>(wbase + t.off_act);
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(128, tick_min_blocks<NW, RPL>()) k_tick(const 
     uint16_t *stage = reinterpret_cast<uint16_t *>(wbase + t.off_stage);
     uint16_t *stage2 = reinterpret_cast<uint16_t *>(wbase + t.off_stage2);
     const int N = c.N, R = t.rec_elems, G = t.group;
-    const bool clip = t.obs_kind == OBS_CLIP, full = t.obs_kind == OBS_FULL;
+    constexpr bool clip = OBS == OBS_CLIP, full = OBS == OBS_FULL;
 
     bool live = true;
     if (ws.over) {
@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(128, tick_min_blocks<NW, RPL>()) k_tick(const 
     }
     if (live) { ws.build_occ(); ws.tick++; ws.acted_mask = 0; }
     bool stopped = !live;
+    bool group_dirty = false;
     for (int i = 0; i < N; i++) {
         bool act = false;
         if (!stopped && !ws.over) {
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(128, tick_min_blocks<NW, RPL>()) k_tick(const 
             if (st == -1) stopped = true;                    // Scene.py:127-128 break
             else if (st == -2) {                             // Scene.py:129-130 return
                 ws.over = 1;
-                if (lane == 0) atomicAdd(c.counters + 1, 1ull);
+                ws.cnt_ended++;
             } else if (st == 1) act = true;
         }
         const size_t rec = (size_t)e * N + i;
@@ -106,32 +107,36 @@ __global__ void __launch_bounds__(128, tick_min_blocks<NW, RPL>()) k_tick(const 
         if (act) {
             TurnOut o;
             const int given = (t.policy == POLICY_GIVEN && t.action) ? (int)t.action[rec] : -1;
-            do_turn<NW, RPL>(ws, i, t.proto, t.policy, given, t.obs_kind, od, nd, o);
-            if (lane == 0) {
-                o_act[i] = (int8_t)o.action; o_done[i] = (uint8_t)o.done; o_rew[i] = o.reward;
-                o_plen[i] = (uint16_t)o.plen; o_slen[i] = (uint16_t)o.slen;
-            }
+            do_turn<NW, RPL, OBS, SHAPED>(ws, i, t.proto, t.policy, given, od, nd, o);
+            // warp-uniform values, stored by every lane (no divergent lane-0 block)
+            o_act[i] = (int8_t)o.action; o_done[i] = (uint8_t)o.done; o_rew[i] = o.reward;
+            o_plen[i] = (uint16_t)o.plen; o_slen[i] = (uint16_t)o.slen;
         } else {
-            if (lane == 0) { o_act[i] = -1; o_done[i] = 0; o_rew[i] = 0.f; o_plen[i] = 0; o_slen[i] = 0xFFFF; }
+            // no turn: the observation records of this AGV are left untouched (the consumer masks
+            // with act_out >= 0); a clip record inside a flush group is zero-filled so that the
+            // group can still go out as one aligned vector store
+            o_act[i] = -1; o_done[i] = 0; o_rew[i] = 0.f; o_plen[i] = 0; o_slen[i] = 0xFFFF;
             if (clip) {
                 if (od) for (int q = lane; q < R; q += 32) od[q] = 0;
                 if (nd) for (int q = lane; q < R; q += 32) nd[q] = 0;
-            } else if (full) {
-                if (od) zero_global(od, R, lane);
-                if (nd) zero_global(nd, R, lane);
             }
         }
+        if (clip) group_dirty |= act;
         if (clip && (((i + 1) & (G - 1)) == 0 || i == N - 1)) {  // G is a power of two
             const int g0 = i & ~(G - 1), nrec = i - g0 + 1;
             const size_t off = ((size_t)e * N + g0) * R;
-            if (t.obs) flush_bytes(reinterpret_cast<uint8_t *>(t.obs + off), reinterpret_cast<uint8_t *>(stage),
-                                   nrec * R * 2, lane);
-            if (t.next_obs) flush_bytes(reinterpret_cast<uint8_t *>(t.next_obs + off),
-                                        reinterpret_cast<uint8_t *>(stage2), nrec * R * 2, lane);
+            if (group_dirty) {
+                if (t.obs) flush_bytes(reinterpret_cast<uint8_t *>(t.obs + off), reinterpret_cast<uint8_t *>(stage),
+                                       nrec * R * 2, lane);
+                if (t.next_obs) flush_bytes(reinterpret_cast<uint8_t *>(t.next_obs + off),
+                                            reinterpret_cast<uint8_t *>(stage2), nrec * R * 2, lane);
+            }
+            group_dirty = false;
         }
     }
     if (live && !ws.over) ws.spawn();
     ws.regs_to_hdr();
+    ws.flush_counters();
     ws.store_block(wbase + t.off_blk, e);
     for (int j = lane; j < N; j += 32) {
         const size_t rec = (size_t)e * N + j;
@@ -228,14 +233,16 @@ __global__ void __launch_bounds__(128) k_step_turn(const DevCfg c, const StepArg
         const int st = ws.turn_state(k);
         if (st == -2) {
             ws.over = 1;
-            if (lane == 0) atomicAdd(c.counters + 1, 1ull);
+            ws.cnt_ended++;
         } else if (st == 1) {
             ws.build_occ();
             const int given = t.action ? (int)t.action[e] : -1;
-            do_turn<NW, RPL>(ws, k, t.proto, POLICY_GIVEN, given, OBS_NONE, nullptr, nullptr, o);
+            if (c.shaped) do_turn<NW, RPL, OBS_NONE, true>(ws, k, t.proto, POLICY_GIVEN, given, nullptr, nullptr, o);
+            else do_turn<NW, RPL, OBS_NONE, false>(ws, k, t.proto, POLICY_GIVEN, given, nullptr, nullptr, o);
             acted = true;
         }
         ws.regs_to_hdr();
+        ws.flush_counters();
         ws.store_block(wbase + t.off_blk, e);
     }
     if (lane == 0) {
@@ -532,9 +539,18 @@ int agv_tick(AgvHandle *h, int32_t proto, int32_t policy, int32_t obs_kind, cons
     t.off_stage = off; off += t.obs ? stage_bytes : 0;
     t.off_stage2 = off; off += t.next_obs ? stage_bytes : 0;
     t.per_warp = off;
-#define CALL(NW_, RPL_) return launch_warps(k_tick<NW_, RPL_>, h->cfg.E, t.per_warp, (cudaStream_t)stream, h->dc, t)
+#define CALL_OS(NW_, RPL_, OBS_, SH_) \
+    return launch_warps(k_tick<NW_, RPL_, OBS_, SH_>, h->cfg.E, t.per_warp, (cudaStream_t)stream, h->dc, t)
+#define CALL(NW_, RPL_)                                                              \
+    do {                                                                             \
+        const bool sh = h->cfg.shaped_reward != 0;                                   \
+        if (t.obs_kind == AGV_OBS_CLIP) { if (sh) CALL_OS(NW_, RPL_, OBS_CLIP, true); else CALL_OS(NW_, RPL_, OBS_CLIP, false); } \
+        else if (t.obs_kind == AGV_OBS_FULL) { if (sh) CALL_OS(NW_, RPL_, OBS_FULL, true); else CALL_OS(NW_, RPL_, OBS_FULL, false); } \
+        else { if (sh) CALL_OS(NW_, RPL_, OBS_NONE, true); else CALL_OS(NW_, RPL_, OBS_NONE, false); } \
+    } while (0)
     DISPATCH(h, CALL);
 #undef CALL
+#undef CALL_OS
 }
 
 int agv_tick_host(AgvHandle *h, int32_t proto, int32_t policy, int32_t obs_kind, const int8_t *action_host,
