@@ -270,7 +270,7 @@ __device__ __forceinline__ int warp_bfs(const Row<NW> (&valid)[RPL], int sx, int
             for (int s = 0; s < RPL; s++) ne |= rany(f[s]);
             if (!__any_sync(FULL, ne)) return A_STOP;
         }
-        while (level < lmin) { bfs_expand<NW, RPL>(f, av, m_up, m_dn); ++level; }
+        // (the up to 3 remaining hit-free levels run in phase 2: one loop body less to fetch)
     }
     // Phase 2: hit test every level.
     for (;;) {

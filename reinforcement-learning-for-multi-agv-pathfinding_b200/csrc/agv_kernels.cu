@@ -83,18 +83,20 @@ __global__ void __launch_bounds__(128, tick_min_blocks<NW, RPL>()) k_tick(const 
         else live = false;
     }
     if (live) { ws.build_occ(); ws.tick++; ws.acted_mask = 0; }
-    bool stopped = !live;
+    // per-AGV outputs default to "no turn"; the turn loop only visits the created prefix and
+    // stops at the first uncreated AGV (Scene.py:127-128) or when the episode is over
+    for (int j = lane; j < N; j += 32) { o_act[j] = -1; o_done[j] = 0; o_rew[j] = 0.f; o_plen[j] = 0; o_slen[j] = 0xFFFF; }
+    __syncwarp();
+    const int n_loop = live ? min(N, ws.n_created) : 0;  // spawn happens after the loop
+    const int8_t *given_row = (t.policy == POLICY_GIVEN && t.action) ? t.action + (size_t)e * N : nullptr;
     bool group_dirty = false;
-    for (int i = 0; i < N; i++) {
+    int i = 0;
+    for (; i < n_loop && !ws.over; i++) {
         bool act = false;
-        if (!stopped && !ws.over) {
-            const int st = ws.turn_state(i);
-            if (st == -1) stopped = true;                    // Scene.py:127-128 break
-            else if (st == -2) {                             // Scene.py:129-130 return
-                ws.over = 1;
-                ws.cnt_ended++;
-            } else if (st == 1) act = true;
-        }
+        if (ws.finished) {                                   // Scene.py:129-130 return
+            ws.over = 1;
+            ws.cnt_ended++;
+        } else act = !((ws.meta_s[i] >> 3) & 1);             // Scene.py:132-134 idle AGVs are skipped
         const size_t rec = (size_t)e * N + i;
         uint16_t *od = nullptr, *nd = nullptr;
         if (clip) {
@@ -106,33 +108,39 @@ __global__ void __launch_bounds__(128, tick_min_blocks<NW, RPL>()) k_tick(const 
         }
         if (act) {
             TurnOut o;
-            const int given = (t.policy == POLICY_GIVEN && t.action) ? (int)t.action[rec] : -1;
+            const int given = given_row ? (int)given_row[i] : -1;
             do_turn<NW, RPL, OBS, SHAPED>(ws, i, t.proto, t.policy, given, od, nd, o);
             // warp-uniform values, stored by every lane (no divergent lane-0 block)
             o_act[i] = (int8_t)o.action; o_done[i] = (uint8_t)o.done; o_rew[i] = o.reward;
             o_plen[i] = (uint16_t)o.plen; o_slen[i] = (uint16_t)o.slen;
-        } else {
-            // no turn: the observation records of this AGV are left untouched (the consumer masks
-            // with act_out >= 0); a clip record inside a flush group is zero-filled so that the
-            // group can still go out as one aligned vector store
-            o_act[i] = -1; o_done[i] = 0; o_rew[i] = 0.f; o_plen[i] = 0; o_slen[i] = 0xFFFF;
-            if (clip) {
-                if (od) for (int q = lane; q < R; q += 32) od[q] = 0;
-                if (nd) for (int q = lane; q < R; q += 32) nd[q] = 0;
+        } else if (clip) {
+            // no turn: observation records of this AGV are left untouched in HBM (the consumer
+            // masks with act_out >= 0); inside a flush group the slot is zero-filled so that the
+            // group still goes out as one aligned vector store
+            if (od) for (int q = lane; q < R; q += 32) od[q] = 0;
+            if (nd) for (int q = lane; q < R; q += 32) nd[q] = 0;
+        }
+        if (clip) {
+            group_dirty |= act;
+            if (((i + 1) & (G - 1)) == 0) {  // G is a power of two: group complete
+                if (group_dirty) {
+                    const size_t off = ((size_t)e * N + (i & ~(G - 1))) * R;
+                    if (t.obs) flush_bytes(reinterpret_cast<uint8_t *>(t.obs + off),
+                                           reinterpret_cast<uint8_t *>(stage), G * R * 2, lane);
+                    if (t.next_obs) flush_bytes(reinterpret_cast<uint8_t *>(t.next_obs + off),
+                                                reinterpret_cast<uint8_t *>(stage2), G * R * 2, lane);
+                }
+                group_dirty = false;
             }
         }
-        if (clip) group_dirty |= act;
-        if (clip && (((i + 1) & (G - 1)) == 0 || i == N - 1)) {  // G is a power of two
-            const int g0 = i & ~(G - 1), nrec = i - g0 + 1;
-            const size_t off = ((size_t)e * N + g0) * R;
-            if (group_dirty) {
-                if (t.obs) flush_bytes(reinterpret_cast<uint8_t *>(t.obs + off), reinterpret_cast<uint8_t *>(stage),
-                                       nrec * R * 2, lane);
-                if (t.next_obs) flush_bytes(reinterpret_cast<uint8_t *>(t.next_obs + off),
-                                            reinterpret_cast<uint8_t *>(stage2), nrec * R * 2, lane);
-            }
-            group_dirty = false;
-        }
+    }
+    if (clip && group_dirty && (i & (G - 1)) != 0) {  // partially filled last group
+        const int g0 = i & ~(G - 1), nrec = i - g0;
+        const size_t off = ((size_t)e * N + g0) * R;
+        if (t.obs) flush_bytes(reinterpret_cast<uint8_t *>(t.obs + off), reinterpret_cast<uint8_t *>(stage),
+                               nrec * R * 2, lane);
+        if (t.next_obs) flush_bytes(reinterpret_cast<uint8_t *>(t.next_obs + off),
+                                    reinterpret_cast<uint8_t *>(stage2), nrec * R * 2, lane);
     }
     if (live && !ws.over) ws.spawn();
     ws.regs_to_hdr();
