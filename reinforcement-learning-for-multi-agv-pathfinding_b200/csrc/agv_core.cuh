@@ -23,6 +23,9 @@ constexpr int POLICY_GIVEN = 0, POLICY_ASTAR = 1, POLICY_GUIDED = 2;
 constexpr int OBS_NONE = 0, OBS_CLIP = 1, OBS_FULL = 2;
 constexpr uint16_t BF16_ONE = 0x3F80;
 constexpr int HDR_BYTES = 32;
+#ifndef AGV_BFS_UNROLL
+#define AGV_BFS_UNROLL 4  // BFS levels per loop body (= period of the empty-frontier test)
+#endif
 
 // Scene state header, first HDR_BYTES of a scene block.
 struct EnvHdr {
@@ -261,10 +264,10 @@ __device__ __forceinline__ int warp_bfs(const Row<NW> (&valid)[RPL], int sx, int
     // before that level: expand without the per-level hit test / vote.
     {
         const int lmin = abs(sx - tx) + abs(sy - ty) - 1;
-        while (level + 4 <= lmin) {
+        while (level + AGV_BFS_UNROLL <= lmin) {
 #pragma unroll
-            for (int u = 0; u < 4; u++) bfs_expand<NW, RPL>(f, av, m_up, m_dn);
-            level += 4;
+            for (int u = 0; u < AGV_BFS_UNROLL; u++) bfs_expand<NW, RPL>(f, av, m_up, m_dn);
+            level += AGV_BFS_UNROLL;
             bool ne = false;
 #pragma unroll
             for (int s = 0; s < RPL; s++) ne |= rany(f[s]);
@@ -275,7 +278,7 @@ __device__ __forceinline__ int warp_bfs(const Row<NW> (&valid)[RPL], int sx, int
     // Phase 2: hit test every level.
     for (;;) {
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < AGV_BFS_UNROLL; u++) {
             bool hit = false;
 #pragma unroll
             for (int s = 0; s < RPL; s++) hit |= rany(rand_(f[s], nb[s]));
