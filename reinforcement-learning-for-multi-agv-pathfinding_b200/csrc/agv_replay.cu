@@ -166,12 +166,33 @@ __global__ void k_tree_set_leaves(ReplayDev r, const double *leaf_new, const lon
     const long long s = leaf_slot[t];
     if (s >= 0) r.tree[s + r.cap - 1] = leaf_new[t];
 }
-__global__ void k_tree_rebuild_level(ReplayDev r, long long lo, long long hi) {
-    const long long v = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= hi) return;
-    const long long n = 2 * r.cap - 1, l = 2 * v + 1;
-    if (l >= n) return;  // a leaf on this level
-    r.tree[v] = r.tree[l] + (l + 1 < n ? r.tree[l + 1] : 0.0);
+// Bottom-up rebuild of all internal nodes in two launches.  k_tree_rebuild_sub: CTA b owns the
+// subtree rooted at heap node (2^d0 - 1) + b and recomputes its levels deepest-first (a node is
+// internal iff its left child exists: the reference's `left >= len(tree)` test, PER.py:29);
+// k_tree_rebuild_top: one CTA finishes the levels above d0.
+__global__ void k_tree_rebuild_sub(ReplayDev r, int d0, int lmax) {
+    const long long n = 2 * r.cap - 1;
+    const long long root = ((1ll << d0) - 1) + blockIdx.x;
+    if (root >= n) return;
+    for (int d = lmax; d >= d0; d--) {
+        const long long first = ((root + 1) << (d - d0)) - 1, count = 1ll << (d - d0);
+        for (long long q = threadIdx.x; q < count; q += blockDim.x) {
+            const long long v = first + q, l = 2 * v + 1;
+            if (v < n && l < n) r.tree[v] = r.tree[l] + (l + 1 < n ? r.tree[l + 1] : 0.0);
+        }
+        __syncthreads();
+    }
+}
+__global__ void k_tree_rebuild_top(ReplayDev r, int d0) {
+    const long long n = 2 * r.cap - 1;
+    for (int d = d0 - 1; d >= 0; d--) {
+        const long long first = (1ll << d) - 1, count = 1ll << d;
+        for (long long q = threadIdx.x; q < count; q += blockDim.x) {
+            const long long v = first + q, l = 2 * v + 1;
+            if (v < n && l < n) r.tree[v] = r.tree[l] + (l + 1 < n ? r.tree[l + 1] : 0.0);
+        }
+        __syncthreads();
+    }
 }
 
 __device__ __forceinline__ void gather_row(const ReplayDev &r, long long s, int q, uint16_t *obs, int8_t *act,
@@ -336,18 +357,15 @@ int agv_replay_push(AgvReplay *r, int64_t n_rows, const int8_t *act_dev, const f
     } else {
         k_tree_set_leaves<<<(unsigned)((n_rows + 255) / 256), 256, 0, st>>>(r->d, r->leaf_new, r->leaf_slot);
         R_LAUNCH_CHECK();
-        // heap levels bottom-up: level L holds nodes [2^L - 1, 2^(L+1) - 1)
+        // heap levels: level L holds nodes [2^L - 1, 2^(L+1) - 1)
         const long long n = 2 * r->d.cap - 1;
-        int top = 0;
-        while (((1ll << (top + 1)) - 1) < n) top++;
-        for (int L = top; L >= 0; L--) {
-            const long long lo = (1ll << L) - 1;
-            long long hi = (1ll << (L + 1)) - 1;
-            if (hi > n) hi = n;
-            if (lo >= r->d.cap - 1 && lo >= hi) continue;
-            const long long cnt = hi - lo;
-            if (cnt <= 0) continue;
-            k_tree_rebuild_level<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(r->d, lo, hi);
+        int lmax = 0;
+        while (((1ll << (lmax + 1)) - 1) < n) lmax++;
+        const int d0 = lmax > 9 ? lmax - 9 : 0;
+        k_tree_rebuild_sub<<<(unsigned)(1ll << d0), 1024, 0, st>>>(r->d, d0, lmax);
+        R_LAUNCH_CHECK();
+        if (d0 > 0) {
+            k_tree_rebuild_top<<<1, 1024, 0, st>>>(r->d, d0);
             R_LAUNCH_CHECK();
         }
     }
