@@ -348,3 +348,87 @@ def test_invalid_arguments(pkg):
     with pytest.raises(L.AgvError):
         sc.set_tasks(np.zeros((2, 2, 4), dtype=np.uint8))  # coordinates out of range
     sc.close()
+
+
+@pytest.mark.parametrize("P", [1, 2, 5])
+def test_clip_window_sizes(pkg, P):
+    """limited visual with padding sizes other than the default 3 (K = 3, 5, 11)"""
+    grid = orc.rect_layout(3, 2, 3, 3, 2)
+    E, N = 6, 5
+    tasks = np.array([orc.make_tasks(grid, random.Random(50 + e)) for e in range(E)], dtype=np.uint8)
+    sc = pkg.BatchedScene(grid, E, N, tasks=tasks, P=P)
+    sc.reset()
+    envs = [orc.Env(grid, tasks[e], N) for e in range(E)]
+    for t in range(60):
+        hdr, _ = sc.get_state()
+        over = hdr[:, 5].astype(bool)
+        if over.any():
+            sc.reset(over.astype(np.uint8))
+            for e in np.nonzero(over)[0]:
+                envs[e].reset()
+        _cmp_tick(pkg, sc, envs, 1, 2, 1, P, want_next=True, tag=("P", P, t))
+    sc.close()
+
+
+def test_edge_scenes(pkg):
+    """no tasks at all, one task for many AGVs, a 1-row corridor, an early max_steps ending"""
+    # T = 0: AGV 0 is created idle, task_finished is raised at creation, the next tick returns
+    grid = orc.rect_layout(2, 1, 1, 1, 1)
+    sc = pkg.BatchedScene(grid, 2, 3, tasks=None)
+    sc.reset()
+    envs = [orc.Env(grid, np.zeros((0, 4), dtype=np.int32), 3) for _ in range(2)]
+    for t in range(3):
+        _cmp_tick(pkg, sc, envs, 1, 2, 0, 3, tag=("T0", t))
+    assert sc.get_state()[0][:, 5].all()
+    sc.close()
+    # corridor 1 x 12 with a storage cell and a picking station, 3 AGVs (they block each other)
+    grid = np.zeros((1, 12), dtype=np.uint8)
+    grid[0, 6] = 1
+    grid[0, 11] = 2
+    tasks = np.array([[[7, 1, 12, 1]]] * 4, dtype=np.uint8)
+    for proto, policy in ((0, 1), (1, 2)):
+        sc = pkg.BatchedScene(grid, 4, 3, tasks=tasks)
+        sc.reset()
+        envs = [orc.Env(grid, tasks[e], 3) for e in range(4)]
+        for t in range(40):
+            _cmp_tick(pkg, sc, envs, proto, policy, 2, 3, want_next=True, tag=("corridor", proto, t))
+        sc.close()
+    # max_steps = 5: every episode ends by the step cap (Scene.py:155)
+    grid = orc.rect_layout(2, 1, 2, 1, 1)
+    tasks = np.array([orc.make_tasks(grid, random.Random(e)) for e in range(4)], dtype=np.uint8)
+    sc = pkg.BatchedScene(grid, 4, 2, tasks=tasks, max_steps=5)
+    sc.reset()
+    envs = [orc.Env(grid, tasks[e], 2, max_steps=5) for e in range(4)]
+    for t in range(7):
+        _cmp_tick(pkg, sc, envs, 1, 2, 1, 3, tag=("cap", t))
+    hdr, _ = sc.get_state()
+    assert hdr[:, 5].all() and (hdr[:, 0] <= 5).all()
+    sc.close()
+
+
+def test_injected_overlapping_state(pkg):
+    """agv_set_state with two created AGVs on one cell (reachable in the reference through the
+    A_star protocol with hand-fed actions): the slow-path ballots must agree with the oracle"""
+    grid = orc.rect_layout(4, 2, 2, 2, 2)
+    E, N = 4, 4
+    tasks = np.array([orc.make_tasks(grid, random.Random(e)) for e in range(E)], dtype=np.uint8)
+    rng = np.random.default_rng(11)
+    for proto in (0, 1):
+        sc = pkg.BatchedScene(grid, E, N, tasks=tasks)
+        sc.reset()
+        envs = [orc.Env(grid, tasks[e], N) for e in range(E)]
+        # A_star protocol, hand-fed actions: AGV 0 steps RIGHT to (2,1) and waits, AGV 1 spawns at
+        # (1,1) and follows onto the same cell (no AGV-AGV test in this protocol), then both wander
+        script = [[1, 4, 4, 4], [4, 1, 4, 4]] + [list(rng.integers(0, 5, size=N)) for _ in range(6)]
+        for t, row in enumerate(script):
+            given = np.tile(np.array(row, dtype=np.int8), (E, 1))
+            _cmp_tick(pkg, sc, envs, 0, 0, 1, 3, given=given, tag=("ov-setup", t))
+            if t == 1:
+                hdr, agv = sc.get_state()
+                assert (agv[:, 0, :2] == agv[:, 1, :2]).all() and (hdr[:, 4] >= 2).all()
+        hdr, agv = sc.get_state()
+        sc.set_state(hdr, agv)  # round trip through agv_set_state keeps the (overlapping) state
+        # now continue with the guided policy under either protocol from the overlapping state
+        for t in range(25):
+            _cmp_tick(pkg, sc, envs, proto, 2, 1, 3, want_next=True, tag=("ov", proto, t))
+        sc.close()
