@@ -200,8 +200,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scenes", type=int, default=0, help="override scenes per GPU")
     ap.add_argument("--spinup", type=int, default=-1, help="untimed ticks before warm-up (default: 2*AGVs)")
-    ap.add_argument("--mode", default="env", choices=["env", "train"],
-                    help="env: fused tick (headline); train: AG-DQN with the CNN in the loop + replay + learner")
+    ap.add_argument("--mode", default="env", choices=["env", "train", "expert"],
+                    help="env: fused tick (headline); train: AG-DQN with the CNN in the loop + replay + learner; "
+                         "expert: A_star-mode rollouts pushed into the device replay buffer (configs[4])")
     ap.add_argument("--obs", default="clip", choices=["clip", "full"],
                     help="clip: limited visual 3x7x7 (AG-DQN, headline); full: 3xHxW (PG/AC/DQN controllers)")
     ap.add_argument("--policy", default="guided", choices=["guided", "astar"],
@@ -299,6 +300,35 @@ def main():
                            "epsilon": 0.8},
                 "gpu_launches": int(lib.agv_launch_count() - l0), "learner_updates": agent.learn_step_counter,
                 "turns_per_step": turns / steps}))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    if args.mode == "expert":
+        # Expert-mode behavioural-cloning rollout collection: BFS expert actions + clip states of
+        # every AGV turn into the device replay buffer (BASELINE configs[4])
+        rp = pkg.DeviceReplay(1 << 22, (3, sc.K, sc.K), device=local_rank)
+        du = importlib.import_module(PKG + ".dist_util")
+        sc.collect_expert(rp, max(warmup, 2 * N))
+        l0 = lib.agv_launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        du.barrier(dev)
+        ev0.record()
+        pushed = sc.collect_expert(rp, steps)
+        ev1.record()
+        du.barrier(dev)
+        ms, turns = du.reduce_timing(ev0.elapsed_time(ev1), int(pushed.item()), dev)
+        if rank == 0:
+            print(json.dumps({
+                "metric": METRIC, "value": turns / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+                "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8/u64 bitboards, bf16 obs", "data": "synthetic",
+                "config": {"workload": "Expert rollouts into device replay: " + desc, "mode": "expert",
+                           "agvs_per_scene": N, "scenes_per_gpu": E, "replay_capacity": 1 << 22,
+                           "row": "clip obs + next obs bf16, action, reward, done"},
+                "gpu_launches": int(lib.agv_launch_count() - l0), "turns_per_step": turns / steps,
+                "replay_entries": rp.info()[0]}))
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()

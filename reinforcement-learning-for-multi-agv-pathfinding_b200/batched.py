@@ -149,6 +149,20 @@ class BatchedScene:
                 "agv_tick_host")
         return {"act": hb["act"], "reward": hb["reward"], "done": hb["done"], "obs": obs, "next_obs": nxt}
 
+    def collect_expert(self, replay, n_ticks: int, obs_kind=L.OBS_CLIP):
+        """Expert-mode rollout collection (ExpertManager.create_data_by_self, batched): `n_ticks`
+        passes of the A_star control mode for every scene; each AGV turn's (state, A* action)
+        pair goes straight from the tick's output tensors into the device replay buffer
+        (reward / next state are stored too, so the same rows also serve DQN-style learners).
+        Returns the number of AGV turns pushed (device tensor)."""
+        turns = torch.zeros((), dtype=torch.int64, device=self.device)
+        for _ in range(n_ticks):
+            o = self.tick(L.PROTO_ASTAR, L.POLICY_ASTAR, obs_kind, want_next=True, want_lens=False)
+            replay.push(o["act"].view(-1), o["reward"].view(-1), o["done"].view(-1),
+                        o["obs"].view(self.E * self.N, -1), o["next_obs"].view(self.E * self.N, -1), None)
+            turns += (o["act"] >= 0).sum()
+        return turns
+
     # ------------------------------------------------------------------ sub-step protocol
     def begin_tick(self):
         L.check(self.lib.agv_begin_tick(self._h, self._stream()), "agv_begin_tick")

@@ -282,3 +282,34 @@ def test_batched_agdqn_agent(pkg):
     assert M.Net()(torch.zeros(2, 3, 7, 7)).shape == (2, 4)
     a.close()
     b.close()
+
+
+def test_expert_rollouts_into_device_replay(pkg):
+    """A_star-mode turns land in the replay buffer in (scene, AGV) order with the expert action"""
+    import torch
+    grid = orc.rect_layout(4, 2, 2, 2, 2)
+    E, N = 8, 4
+    tasks = np.array([orc.make_tasks(grid, random.Random(e)) for e in range(E)], dtype=np.uint8)
+    sc = pkg.BatchedScene(grid, E, N, tasks=tasks)
+    sc.reset()
+    rp = pkg.DeviceReplay(4096, (3, 7, 7))
+    envs = [orc.Env(grid, tasks[e], N) for e in range(E)]
+    exp = []
+    for t in range(20):
+        for env in envs:
+            n, a, r, d, pl, sl, ob, nx = env.tick_obs(orc.PROTO_ASTAR, orc.POLICY_ASTAR, obs_kind=1, P=3, want_next=True)
+            for i in range(N):
+                if a[i] >= 0:
+                    exp.append((int(a[i]), float(r[i]), ob[i], nx[i]))
+    pushed = int(sc.collect_expert(rp, 20))
+    assert pushed == len(exp) and rp.info()[0] == len(exp)
+    b = rp.gather(torch.arange(len(exp)))
+    act = b["act"].cpu().numpy()
+    rew = b["reward"].cpu().numpy()
+    obs = b["obs"].float().cpu().numpy()
+    nxt = b["next_obs"].float().cpu().numpy()
+    for q, (a, r, ob, nx) in enumerate(exp):
+        assert act[q] == a and rew[q] == np.float32(r)
+        assert np.array_equal(obs[q], ob) and np.array_equal(nxt[q], nx)
+    sc.close()
+    rp.close()
