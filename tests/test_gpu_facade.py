@@ -313,3 +313,41 @@ def test_expert_rollouts_into_device_replay(pkg):
         assert np.array_equal(obs[q], ob) and np.array_equal(nxt[q], nx)
     sc.close()
     rp.close()
+
+
+def test_q_values_within_bf16_tolerance(pkg):
+    """north star: Q-values within a stated bf16/fp32 tolerance.  Reference side: the states the
+    live reference's StateManager produced (fixture), fp32 forward on the CPU.  Our side: the CUDA
+    encoder's bf16 states, bf16-autocast channels-last forward on the GPU, same weights.
+    Tolerance: |dQ| <= 2e-2 * max|Q|.  The states themselves are bit-identical."""
+    import importlib
+    import torch
+    M = importlib.import_module("reinforcement-learning-for-multi-agv-pathfinding_b200.algorithm.MADQN_structure.MADQN")
+    torch.manual_seed(0)
+    net = M.Net()
+    ref_obs, infos, vehs = [], [], []
+    for ep in golden("intelligent.json"):
+        names = ["veh%d" % (i + 1) for i in range(ep["n_agv"])]
+        for t in ep["turns"]:
+            if "obs_clip" in t and ep["grid"] == golden("intelligent.json")[0]["grid"]:
+                ref_obs.append(t["obs_clip"])
+                infos.append([ep["grid"]] + [[names[j], [v[0], v[1]], [v[2], v[3]], bool(v[4])]
+                                             for j, v in enumerate(t["before"])])
+                vehs.append(names[t["i"]])
+    assert len(ref_obs) >= 8
+    x_ref = torch.tensor(np.array(ref_obs, dtype=np.float32))
+    with torch.no_grad():
+        q_ref = net(x_ref)
+    ours = pkg.StateManager().create_state_batch(infos, vehs, obs_clip=True)
+    assert np.array_equal(ours, x_ref.numpy())  # integer part: exact
+    gnet = M.Net().cuda()
+    gnet.load_state_dict(net.state_dict())
+    gnet = gnet.to(memory_format=torch.channels_last)
+    xb = torch.tensor(ours).cuda().to(torch.bfloat16)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        q_bf16 = gnet(xb.contiguous(memory_format=torch.channels_last)).float().cpu()
+    with torch.no_grad():
+        q_fp32 = gnet(xb.float()).cpu()
+    scale = q_ref.abs().max()
+    assert (q_fp32 - q_ref).abs().max() <= 1e-4 * scale          # fp32 on the GPU vs fp32 on the CPU
+    assert (q_bf16 - q_ref).abs().max() <= 2e-2 * scale          # bf16 autocast, stated tolerance
