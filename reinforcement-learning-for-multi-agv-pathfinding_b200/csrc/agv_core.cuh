@@ -173,17 +173,6 @@ __device__ __forceinline__ bool test_bit_local(const Row<NW> (&rows)[RPL], int r
 }
 
 // ------------------------------------------------------------------ BFS
-// Target-rooted bit-parallel BFS over `valid`; stops at the first level whose
-// frontier touches a neighbour of the start cell.  Equivalent to
-// FindPathAstar(valid, start, target).run_astar_method() (astar.py:66-153) as far
-// as its callers use it (Explorer.py:286-302, MADQN.py:192-200): returns
-// action_list[0] (STOP when not found or empty) and len(action_list) in `len`.
-// The reference's open list is FIFO (all_cost is never assigned, astar.py:14,86)
-// and re-parents on ties (astar.py:108-117), which makes the path the
-// lexicographically largest shortest path under LEFT < UP < DOWN < RIGHT
-// (neighbour order astar.py:33-38); hence the priority RIGHT, DOWN, UP, LEFT
-// among start neighbours one step closer to the target (SURVEY.md App. A.8).
-// Coordinates are 0-based.  All lanes must call; the result is warp-uniform.
 // multiply both 32-bit halves by m in {0,1}: boundary masking on the FMA pipe (IMAD)
 // instead of SEL on the (saturated) ALU pipe
 template <int NW>
@@ -234,6 +223,17 @@ __device__ __forceinline__ void bfs_expand(Row<NW> (&f)[RPL], Row<NW> (&av)[RPL]
     for (int s = 0; s < RPL; s++) { av[s] = rsub_subset(av[s], n[s]); f[s] = n[s]; }
 }
 
+// Target-rooted bit-parallel BFS over `valid`; stops at the first level whose
+// frontier touches a neighbour of the start cell.  Equivalent to
+// FindPathAstar(valid, start, target).run_astar_method() (astar.py:66-153) as far
+// as its callers use it (Explorer.py:286-302, MADQN.py:192-200): returns
+// action_list[0] (STOP when not found or empty) and len(action_list) in `len`.
+// The reference's open list is FIFO (all_cost is never assigned, astar.py:14,86)
+// and re-parents on ties (astar.py:108-117), which makes the path the
+// lexicographically largest shortest path under LEFT < UP < DOWN < RIGHT
+// (neighbour order astar.py:33-38); hence the priority RIGHT, DOWN, UP, LEFT
+// among start neighbours one step closer to the target (SURVEY.md App. A.8).
+// Coordinates are 0-based.  All lanes must call; the result is warp-uniform.
 template <int NW, int RPL>
 __device__ __forceinline__ int warp_bfs(const Row<NW> (&valid)[RPL], int sx, int sy, int tx, int ty, int H, int W,
                                         int lane, int &len) {

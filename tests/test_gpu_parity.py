@@ -432,3 +432,34 @@ def test_injected_overlapping_state(pkg):
         for t in range(25):
             _cmp_tick(pkg, sc, envs, proto, 2, 1, 3, want_next=True, tag=("ov", proto, t))
         sc.close()
+
+
+def test_c_abi_from_plain_c(pkg, tmp_path):
+    """the C ABI driven by a plain C program (no Python / torch in the loop)"""
+    import os
+    import subprocess
+    from conftest import ROOT
+    exe = str(tmp_path / "abi_smoke")
+    pkg_dir = os.path.dirname(pkg._lib.LIB_PATH)
+    cuda = "/usr/local/cuda"
+    subprocess.check_call(["gcc", "-O1", "-o", exe, os.path.join(ROOT, "tests", "c_abi", "abi_smoke.c"),
+                           "-I" + os.path.join(ROOT, "include"), "-I" + cuda + "/include", "-L" + pkg_dir,
+                           "-L" + cuda + "/lib64", "-lagv_b200", "-lcudart", "-Wl,-rpath," + pkg_dir,
+                           "-Wl,-rpath," + cuda + "/lib64"])
+    grid = orc.rect_layout(4, 2, 2, 2, 2)
+    E, N, ticks = 2, 4, 50
+    tasks = np.array([orc.make_tasks(grid, random.Random(e)) for e in range(E)], dtype=np.uint8)
+    T = tasks.shape[1]
+    inp = "%d %d %d %d %d %d\n" % (grid.shape[0], grid.shape[1], E, N, T, ticks)
+    inp += " ".join(str(int(v)) for v in grid.ravel()) + "\n" + " ".join(str(int(v)) for v in tasks.ravel()) + "\n"
+    out = subprocess.run([exe], input=inp, capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    envs = [orc.Env(grid, tasks[e], N) for e in range(E)]
+    turns = 0
+    for t in range(ticks):
+        exp = []
+        for env in envs:
+            n, a, r, d, pl, sl, _, _ = env.tick_obs(orc.PROTO_INTELLIGENT, orc.POLICY_GUIDED)
+            turns += n
+            exp += ["%d:%g" % (int(a[i]), float(np.float32(r[i]))) for i in range(N)]
+        assert out[t].split() == exp, t
+    assert out[-1].startswith("turns %d " % turns)
