@@ -200,9 +200,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scenes", type=int, default=0, help="override scenes per GPU")
     ap.add_argument("--spinup", type=int, default=-1, help="untimed ticks before warm-up (default: 2*AGVs)")
-    ap.add_argument("--mode", default="env", choices=["env", "train", "expert"],
+    ap.add_argument("--mode", default="env", choices=["env", "train", "expert", "substep"],
                     help="env: fused tick (headline); train: AG-DQN with the CNN in the loop + replay + learner; "
-                         "expert: A_star-mode rollouts pushed into the device replay buffer (configs[4])")
+                         "expert: A_star-mode rollouts pushed into the device replay buffer (configs[4]); "
+                         "substep: the per-AGV callback protocol (encode -> step per AGV index) replayed "
+                         "from one CUDA graph per tick")
     ap.add_argument("--obs", default="clip", choices=["clip", "full"],
                     help="clip: limited visual 3x7x7 (AG-DQN, headline); full: 3xHxW (PG/AC/DQN controllers)")
     ap.add_argument("--policy", default="guided", choices=["guided", "astar"],
@@ -300,6 +302,59 @@ def main():
                            "epsilon": 0.8},
                 "gpu_launches": int(lib.agv_launch_count() - l0), "learner_updates": agent.learn_step_counter,
                 "turns_per_step": turns / steps}))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    if args.mode == "substep":
+        # the network-in-the-loop decomposition without a network: begin_tick, then for every AGV
+        # index k: agv_encode(k) + agv_step_turn(k, action = -1 -> A* guidance), end_tick.  2N+2
+        # launches per tick, captured once into a CUDA graph and replayed (launch-latency bound).
+        du = importlib.import_module(PKG + ".dist_util")
+        minus1 = torch.full((E,), -1, dtype=torch.int8, device=dev)
+
+        def tick_substeps():
+            sc.begin_tick()
+            for k in range(N):
+                sc.encode(k, OBS)
+                sc.step_turn(k, PROTO, minus1)
+            sc.end_tick()
+
+        for _ in range(max(3, warmup)):
+            tick_substeps()
+        torch.cuda.synchronize()
+        results = {}
+        for label in ("eager", "graph"):
+            if label == "graph":
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    tick_substeps()
+                run = g.replay
+            else:
+                run = tick_substeps
+            for _ in range(3):
+                run()
+            sc.counters()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            du.barrier(dev)
+            ev0.record()
+            for _ in range(steps):
+                run()
+            ev1.record()
+            du.barrier(dev)
+            ms, turns = du.reduce_timing(ev0.elapsed_time(ev1), sc.counters()[0], dev)
+            results[label] = (turns / (ms * 1e-3), ms / steps, turns / steps)
+        if rank == 0:
+            v, msps, tps = results["graph"]
+            print(json.dumps({
+                "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+                "ms_per_step": msps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u8/u64 bitboards, bf16 obs", "data": "synthetic",
+                "config": {"workload": "sub-step protocol (CUDA graph): " + desc, "mode": "substep",
+                           "launches_per_tick": 2 * N + 2, "agvs_per_scene": N, "scenes_per_gpu": E},
+                "eager": {"value": results["eager"][0], "ms_per_step": results["eager"][1]},
+                "gpu_launches": (2 * N + 2) * steps, "turns_per_step": tps}))
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()

@@ -441,13 +441,24 @@ struct WarpScene {
     // (no AGV-AGV test, Scene.py:159-162) or agv_set_state; while it is false the per-turn
     // "is another AGV on this cell" ballots reduce to one occupancy-bit test.
     __device__ __forceinline__ void build_occ() {
-#pragma unroll
-        for (int s = 0; s < RPL; s++) occ[s] = rzero<NW>();
+        // parallel over AGVs: every lane ORs the cells of its AGVs into the shared scratch rows
+        // (vrow_s), then picks up the rows it owns; the value returned by atomicOr tells whether
+        // the cell was already taken (two created AGVs on one cell)
+        for (int q = lane; q < c.H * NW; q += 32) vrow_s[q] = 0ull;
+        __syncwarp();
         bool dup = false;
-        for (int j = 0; j < n_created; j++) {
-            const int p = pos_s[j];
-            dup |= test_bit_local<NW, RPL>(occ, (p >> 8) - 1, (p & 255) - 1, lane);
-            set_bit<NW, RPL>(occ, (p >> 8) - 1, (p & 255) - 1, lane);
+        for (int j = lane; j < n_created; j += 32) {
+            const int p = pos_s[j], cc = (p & 255) - 1, r = (p >> 8) - 1;
+            const unsigned long long bit = 1ull << (cc & 63);
+            const unsigned long long old = atomicOr(reinterpret_cast<unsigned long long *>(vrow_s) + r * NW + (cc >> 6), bit);
+            dup |= (old & bit) != 0ull;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < RPL; s++) {
+            const int r = lane * RPL + s;
+#pragma unroll
+            for (int i = 0; i < NW; i++) occ[s].w[i] = r < c.H ? vrow_s[r * NW + i] : 0ull;
         }
         overlap = __any_sync(FULL, dup);
     }
