@@ -463,3 +463,48 @@ def test_c_abi_from_plain_c(pkg, tmp_path):
             exp += ["%d:%g" % (int(a[i]), float(np.float32(r[i]))) for i in range(N)]
         assert out[t].split() == exp, t
     assert out[-1].startswith("turns %d " % turns)
+
+
+def test_output_buffers_are_not_overrun(pkg):
+    """compute-sanitizer is closed on this pool, so out-of-bounds stores are hunted with guard
+    bands: every output tensor of agv_tick / agv_encode is a window into a larger buffer filled
+    with a sentinel; the bands around the window must be untouched (odd E, N and unaligned
+    record sizes on purpose)."""
+    import ctypes as C
+    import torch
+    L = pkg._lib
+    for (gridf, E, N, P, kind) in ((lambda: orc.rect_layout(4, 2, 2, 2, 2), 7, 3, 3, 1),
+                                   (lambda: orc.README_9x9, 5, 5, 2, 2),
+                                   (lambda: orc.rect_layout(6, 2, 9, 20, 8), 3, 37, 3, 1),
+                                   (lambda: orc.rect_layout(6, 2, 9, 20, 8), 2, 9, 3, 2)):
+        grid = gridf()
+        tasks = np.array([orc.make_tasks(grid, random.Random(e)) for e in range(E)], dtype=np.uint8)
+        sc = pkg.BatchedScene(grid, E, N, tasks=tasks, P=P, auto_reset=True)
+        sc.reset()
+        G = 4096  # guard elements on each side
+        R = int(np.prod(sc.obs_shape(kind)))
+
+        def guarded(n, dtype, fill):
+            buf = torch.full((n + 2 * G,), fill, dtype=dtype, device=sc.device)
+            return buf, buf[G:G + n]
+
+        bufs = {k: guarded(n, dt, f) for k, (n, dt, f) in {
+            "act": (E * N, torch.int8, 77), "reward": (E * N, torch.float32, 1234.5),
+            "done": (E * N, torch.uint8, 201), "plen": (E * N, torch.int16, 12345), "slen": (E * N, torch.int16, 12345),
+            "obs": (E * N * R, torch.bfloat16, 7.0), "next_obs": (E * N * R, torch.bfloat16, 7.0)}.items()}
+        out = {k: v[1].view((E, N) + (sc.obs_shape(kind) if "obs" in k else ())) for k, v in bufs.items()}
+        for t in range(2 * N + 6):
+            sc.tick(pkg.PROTO_INTELLIGENT, pkg.POLICY_GUIDED, kind, want_next=True, out=out)
+        # sub-step encoders into a guarded [E, R] window
+        eb, ew = guarded(E * R, torch.bfloat16, 7.0)
+        wb, ww = guarded(E, torch.uint8, 201)
+        st = C.c_void_p(torch.cuda.current_stream(sc.device).cuda_stream)
+        sc.begin_tick()
+        for k in range(N):
+            L.check(sc.lib.agv_encode(sc._h, k, kind, 0, C.c_void_p(ew.data_ptr()), C.c_void_p(ww.data_ptr()), st))
+        torch.cuda.synchronize()
+        for name, (buf, win) in list(bufs.items()) + [("enc", (eb, ew)), ("will", (wb, ww))]:
+            fill = buf[0].item()
+            assert (buf[:G] == fill).all() and (buf[-G:] == fill).all(), (name, E, N, kind)
+        assert set(out["obs"].float().unique().tolist()) <= {0.0, 1.0, 7.0}
+        sc.close()
