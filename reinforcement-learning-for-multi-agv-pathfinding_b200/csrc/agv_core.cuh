@@ -612,8 +612,28 @@ struct WarpScene {
             dst[idx] = v ? BF16_ONE : (uint16_t)0;
         }
     }
+    // K = 7 (the reference's default padding 3): 49 window cells, at most two per lane, whose
+    // window coordinates are compile-time functions of the lane; three stores per cell.
+    __device__ __forceinline__ void encode_clip7(uint16_t *dst, const Agv &a) const {
+        constexpr int K = 7, P = 3, KK = 49;
+        const int cx = a.x - 1, cy = a.y - 1;
+        const int tdx = max(-P, min(P, a.tx - a.x)) + P, tdy = max(-P, min(P, a.ty - a.y)) + P;
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int cell = lane + 32 * q;
+            if (cell < KK) {
+                const int wy = cell / K, wx = cell - wy * K;
+                const int r = cy - P + wy, cc = cx - P + wx;
+                bool v = false;
+                if (r >= 0 && r < c.H && cc >= 0 && cc < c.W) v = (vrow_s[r * NW + (cc >> 6)] >> (cc & 63)) & 1ull;
+                dst[cell] = (cell == P * K + P) ? BF16_ONE : (uint16_t)0;
+                dst[KK + cell] = (wy == tdy && wx == tdx) ? BF16_ONE : (uint16_t)0;
+                dst[2 * KK + cell] = v ? BF16_ONE : (uint16_t)0;
+            }
+        }
+    }
     __device__ __forceinline__ void encode_clip(uint16_t *dst, const Agv &a) const {
-        if (c.K == 7) encode_clip_impl<7>(dst, a);
+        if (c.K == 7) encode_clip7(dst, a);
         else encode_clip_impl<0>(dst, a);
     }
     // StateManager.create_state(obs_clip=False) straight to a [3,H,W] bf16 record in HBM.
