@@ -57,11 +57,16 @@ struct StepArgs {
 // resident CTAs per SM the register budget is tuned for (ptxas -v: no spills at these bounds)
 template <int NW, int RPL>
 constexpr int tick_min_blocks() {
-#ifdef AGV_TICK_MINB
-    return NW * RPL <= 2 ? AGV_TICK_MINB : (NW * RPL <= 4 ? 4 : 2);
-#else
-    return NW * RPL <= 2 ? 6 : (NW * RPL <= 4 ? 4 : 2);
+#ifndef AGV_TICK_MINB
+#define AGV_TICK_MINB 6   // rows fit 2 u64 per lane: 80 registers, no spills
 #endif
+#ifndef AGV_TICK_MINB4
+#define AGV_TICK_MINB4 4  // 4 u64 per lane
+#endif
+#ifndef AGV_TICK_MINB8
+#define AGV_TICK_MINB8 2  // 8 u64 per lane (128 x 128)
+#endif
+    return NW * RPL <= 2 ? AGV_TICK_MINB : (NW * RPL <= 4 ? AGV_TICK_MINB4 : AGV_TICK_MINB8);
 }
 
 template <int NW, int RPL, int OBS, bool SHAPED>
