@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(128) k_bfs_action(const DevCfg c, const StepAr
         Row<NW> v[RPL];
         if (t.matrix == 0) ws.valid_a(a, v);
         else ws.valid_b(a, k, v);
-        action = warp_bfs<NW, RPL>(v, a.x - 1, a.y - 1, a.tx - 1, a.ty - 1, c.H, c.W, lane, plen);
+        action = warp_path<NW, RPL>(v, a.x - 1, a.y - 1, a.tx - 1, a.ty - 1, c.H, c.W, lane, plen);
     }
     if (lane == 0) {
         if (t.action_out) t.action_out[e] = (int8_t)action;
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(128) k_bfs_batch(int B, int H, int W, const ui
     rows_from_bytes<NW, RPL>(valid + (size_t)b * H * W, H, W, lane, v);
     const int sx = start[2 * b], sy = start[2 * b + 1], tx = target[2 * b], ty = target[2 * b + 1];
     int len = 0;
-    const int a = warp_bfs<NW, RPL>(v, sx, sy, tx, ty, H, W, lane, len);
+    const int a = warp_path<NW, RPL>(v, sx, sy, tx, ty, H, W, lane, len);
     if (lane == 0) {
         if (action) action[b] = (int8_t)a;
         if (pathlen) pathlen[b] = len;
