@@ -12,10 +12,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libagv_b200.so")
-SOURCES = ["agv_kernels.cu", "agv_replay.cu"]
-HEADERS = ["agv_core.cuh", os.path.join("..", "..", "include", "agv_b200.h")]
+SOURCES = ["agv_kernels.cu", "agv_lanes.cu", "agv_replay.cu"]
+HEADERS = ["agv_core.cuh", "agv_lanes.cuh", os.path.join("..", "..", "include", "agv_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC"]
+OBJ_DIR = os.path.join(HERE, "build")
 
 
 def _nvcc():
@@ -36,14 +37,30 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
-          [os.path.join(CSRC, s) for s in SOURCES]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    # one object per translation unit, compiled in parallel and only when stale, then one link
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    hdr_t = max(os.path.getmtime(os.path.join(CSRC, h)) for h in HEADERS)
+    extra = os.environ.get("AGV_NVCC_EXTRA", "").split()
+    jobs = []
+    for s in SOURCES:
+        src, obj = os.path.join(CSRC, s), os.path.join(OBJ_DIR, s.replace(".cu", ".o"))
+        stale = force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_t,
+                                                                              os.path.getmtime(os.path.abspath(__file__)))
+        if stale:
+            cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            jobs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    for s, p in jobs:
+        out, err = p.communicate()
+        if p.returncode != 0:
+            sys.stderr.write(out + err)
+            raise RuntimeError("nvcc failed compiling %s" % s)
+        if verbose:
+            sys.stderr.write(err)
+    objs = [os.path.join(OBJ_DIR, s.replace(".cu", ".o")) for s in SOURCES]
+    r = subprocess.run([_nvcc(), "-shared", "-o", LIB] + objs, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed building %s" % LIB)
-    if verbose:
-        sys.stderr.write(r.stderr)
+        raise RuntimeError("nvcc failed linking %s" % LIB)
     return LIB
 
 

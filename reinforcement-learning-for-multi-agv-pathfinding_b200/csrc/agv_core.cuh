@@ -396,8 +396,10 @@ __device__ __forceinline__ int warp_monotone(const Row<NW> (&valid)[RPL], int sx
 #pragma unroll
         for (int i = 0; i < NW; i++) vr.w[i] = __shfl_sync(FULL, (unsigned long long)mine.w[i], ol) & box.w[i];
         const Row<NW> now = rfill_up(rand_(reach, vr), vr);  // vertical step, then horizontal spread
-        if (!rany(now)) return -1;                            // (warp-uniform: every lane holds the same rows)
+        // the start's own row may come out empty when the start cell itself is invalid (matrix (a)
+        // blocks every explorer, Explorer.py:274-283) while `prev` still holds the vertical neighbour
         if (r == sy) { reach = now; break; }
+        if (!rany(now)) return -1;                            // (warp-uniform: every lane holds the same rows)
         prev = now;
         reach = now;
         r -= dys;

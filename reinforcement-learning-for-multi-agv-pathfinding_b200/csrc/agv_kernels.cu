@@ -1,6 +1,6 @@
 // agv_kernels.cu -- kernels + C ABI (include/agv_b200.h) of the batched scene.
 // sm_100a only.  See agv_core.cuh for the warp-per-scene device core.
-#include "agv_core.cuh"
+#include "agv_lanes.cuh"
 #include "../../include/agv_b200.h"
 
 #include <atomic>
@@ -11,6 +11,8 @@
 #include <vector>
 
 namespace agv {
+
+int lanes_tick(const DevCfg &dc, int NW, int RPL, const LaneArgs &t, cudaStream_t st);  // agv_lanes.cu
 
 static std::atomic<uint64_t> g_launches{0};
 static int g_last_cuda = 0;
@@ -388,6 +390,13 @@ static int warps_per_cta() {
     return v;
 }
 
+// fused-tick implementation: "lanes" (lane-per-scene, agv_lanes.cuh; default) or "warp"
+// (warp-per-scene k_tick).  Both are bit-identical; AGV_TICK_IMPL selects for A/B runs and tests.
+static bool tick_impl_lanes() {
+    const char *e = getenv("AGV_TICK_IMPL");
+    return !(e && strcmp(e, "warp") == 0);
+}
+
 template <typename K, typename... Args>
 static int launch_warps(K kernel, int n_warps, size_t smem_per_warp, cudaStream_t st, Args... args) {
     const int WARPS_PER_CTA = warps_per_cta();
@@ -533,6 +542,14 @@ int agv_tick(AgvHandle *h, int32_t proto, int32_t policy, int32_t obs_kind, cons
     t.obs = (uint16_t *)obs_dev; t.next_obs = (uint16_t *)next_obs_dev;
     const int N = h->cfg.N;
     t.rec_elems = obs_elems(h, t.obs_kind);
+    if (tick_impl_lanes()) {
+        LaneArgs la; memset(&la, 0, sizeof(la));
+        la.proto = t.proto; la.policy = t.policy; la.obs_kind = t.obs_kind;
+        la.action = t.action; la.act_out = t.act_out; la.reward = t.reward; la.done = t.done;
+        la.plen = t.plen; la.slen = t.slen; la.obs = t.obs; la.next_obs = t.next_obs; la.rec_elems = t.rec_elems;
+        const int rc = lanes_tick(h->dc, h->NW, h->RPL, la, (cudaStream_t)stream);
+        if (rc != AGV_E_UNSUPPORTED) return rc;  // scenes too large for a lane-per-scene warp: warp-per-scene path
+    }
     t.group = 1;
     if (t.obs_kind == AGV_OBS_CLIP) {
         const int rb = t.rec_elems * 2;
