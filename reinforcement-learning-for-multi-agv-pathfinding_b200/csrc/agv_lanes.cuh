@@ -32,6 +32,7 @@ struct LaneArgs {
     int off_occm;    // same, columns mirrored (c -> 64*NW-1-c)
     int occ_stride;  // in u64 (odd)
     int off_vrow;    // u64 [H*NW]: matrix (b) of the scene being encoded
+    int off_queue;   // LaneQueue (worker-warp variant)
     int off_zero;    // u64 [H*NW] of zeros: "occupancy" of a matrix that does not block the explorers
 };
 
@@ -79,20 +80,29 @@ __device__ __forceinline__ int lane_monotone(bool need, const uint64_t *tab, int
         alive = n == 0 || rany(reach);
     }
     const int nmax = __reduce_max_sync(FULL, alive ? n : 0);
-#pragma unroll 2
+    // Branch-free body: the row loads do not depend on the DP state, so with the state update
+    // done by selects the compiler can unroll and hoist them off the dependent chain
+    // (LDS latency was ~2/3 of the time per row).  Finished lanes re-read their last row.
+    const int nl = alive ? n : 0;
+    if (!alive) { bp = tab; op = tab; }
+#pragma unroll 4
     for (int it = 1; it <= nmax; it++) {
-        if (alive && it <= n) {
-            bp += step; op += step;
-            Row<NW> b = ldrow<NW>(bp);
-            const Row<NW> o = ldrow<NW>(op);
+        const int k = min(it, nl) * step;
+        Row<NW> b = ldrow<NW>(bp + k);
+        const Row<NW> o = ldrow<NW>(op + k);
 #pragma unroll
-            for (int i = 0; i < NW; i++) b.w[i] = b.w[i] & ~o.w[i] & box.w[i];
-            const Row<NW> now = rfill_up(rand_(reach, b), b);
-            prev = reach; reach = now;
-            // the start's own row may come out empty (the start cell is occupied by the AGV itself,
-            // hence invalid) while the vertical neighbour in `prev` is still on a path
-            alive = it == n || rany(now);
+        for (int i = 0; i < NW; i++) b.w[i] = b.w[i] & ~o.w[i] & box.w[i];
+        const Row<NW> now = rfill_up(rand_(reach, b), b);
+        const bool upd = alive && it <= nl;
+        // the start's own row may come out empty (the start cell is occupied by the AGV itself,
+        // hence invalid) while the vertical neighbour in `prev` is still on a path
+        const bool live = it == nl || rany(now);
+#pragma unroll
+        for (int i = 0; i < NW; i++) {
+            prev.w[i] = upd ? reach.w[i] : prev.w[i];
+            reach.w[i] = upd ? now.w[i] : reach.w[i];
         }
+        alive = upd ? live : alive;
     }
     len = 0;
     int act = -1;
@@ -244,8 +254,76 @@ __device__ __forceinline__ void coop_encode_full(uint16_t *dst, const uint64_t *
     }
 }
 
+// ------------------------------------------------------------------ warp-cooperative pieces
+// (run either by the scene warp itself or by a worker warp of the same CTA)
+constexpr int Q_EXIT = 0, Q_BFS = 1, Q_ENC7 = 2, Q_ENCG = 3;
+constexpr int BAR_GO = 1, BAR_DONE = 2;
+struct LaneQueue {
+    int kind, n, i, which;
+    uint4 req[32];
+    unsigned res[32];
+};
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// BFS of one scene.  pk = sx | sy<<7 | tx<<14 | ty<<21 | loaded<<28 | blocks<<29 (0-based cells)
+template <int NW, int RPL>
+__device__ __forceinline__ int coop_bfs(unsigned pk, const uint64_t *tab, int HN, const uint64_t *oj, int H, int W,
+                                        int lane, int &len) {
+    const int jsx = pk & 127, jsy = (pk >> 7) & 127, jtx = (pk >> 14) & 127, jty = (pk >> 21) & 127;
+    const int jl = (pk >> 28) & 1;
+    const uint64_t jom = (pk >> 29) & 1 ? ~0ull : 0ull;
+    const uint64_t *bj = tab + jl * HN;
+    Row<NW> v[RPL];
+#pragma unroll
+    for (int s = 0; s < RPL; s++) {
+        const int r = lane * RPL + s;
+        v[s] = rzero<NW>();
+        if (r < H) {
+#pragma unroll
+            for (int i = 0; i < NW; i++) {
+                uint64_t b = bj[r * NW + i];
+                if (r == jty && i == (jtx >> 6)) b |= 1ull << (jtx & 63);
+                v[s].w[i] = b & ~(oj[r * NW + i] & jom);
+            }
+        }
+    }
+    return warp_bfs<NW, RPL>(v, jsx, jsy, jtx, jty, H, W, lane, len);
+}
+
+// generic observation record of one scene: materialise matrix (b) in `vrow`, then encode.
+// pk = x | y<<8 | tx<<16 | ty<<24 (1-based), fl = loaded | shared<<1
+template <int NW, int OBS>
+__device__ __forceinline__ void coop_encode(unsigned pk, unsigned fl, const uint64_t *tab, int HN, const uint64_t *oj,
+                                            uint64_t *vrow, int H, int W, int K, uint16_t *dst, int lane) {
+    const int jx = pk & 255, jy = (pk >> 8) & 255, jtx = (pk >> 16) & 255, jty = pk >> 24;
+    const int jl = fl & 1;
+    const bool jshared = fl & 2;
+    const uint64_t *bj = tab + jl * HN;
+    for (int r = lane; r < H; r += 32) {
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+            uint64_t b = bj[r * NW + w], o = oj[r * NW + w];
+            if (r == jy - 1 && w == ((jx - 1) >> 6)) {
+                b |= 1ull << ((jx - 1) & 63);
+                if (!jshared) o &= ~(1ull << ((jx - 1) & 63));
+            }
+            if (r == jty - 1 && w == ((jtx - 1) >> 6)) b |= 1ull << ((jtx - 1) & 63);
+            vrow[r * NW + w] = b & ~o;
+        }
+    }
+    __syncwarp();
+    if (OBS == OBS_CLIP) coop_encode_clip<NW>(dst, vrow, H, W, K, jx, jy, jtx, jty, lane);
+    else coop_encode_full<NW>(dst, vrow, H, W, jx, jy, jtx, jty, lane);
+    __syncwarp();
+}
+
 // ------------------------------------------------------------------ one scene per lane
-template <int NW, int RPL, int SPW>
+template <int NW, int RPL, int SPW, int NWK>
 struct LaneScene {
     static constexpr int WB = 64 * NW;
     const DevCfg &c;
@@ -265,10 +343,12 @@ struct LaneScene {
     int n_created, finished, over;
     uint64_t acted_mask;
     bool overlap;
+    bool inflight;  // a request batch is with the worker warps (warp-uniform)
+    long long pbfs = 0, pnb = 0;  // profiling builds: cycles / count of BFS sections
     uint32_t cnt_turns, cnt_ended, cnt_bad;
 
     __device__ __forceinline__ LaneScene(const DevCfg &cfg, const LaneArgs &args, uint8_t *sm, int lane_, int e0)
-        : c(cfg), t(args), lane(lane_), smem(sm), overlap(true), cnt_turns(0), cnt_ended(0), cnt_bad(0) {
+        : c(cfg), t(args), lane(lane_), smem(sm), overlap(true), inflight(false), cnt_turns(0), cnt_ended(0), cnt_bad(0) {
         e = e0 + lane;
         has = lane < SPW && e < c.E;
         HN = c.H * NW;
@@ -313,27 +393,23 @@ struct LaneScene {
         }
     }
     __device__ __forceinline__ void load_blocks(int e0) {
-        const int nsc = min(SPW, c.E - e0), wps = c.env_stride >> 2, total = nsc * wps;
+        const int nsc = min(SPW, c.E - e0), wps = c.env_stride >> 2;
         const uint32_t *src = reinterpret_cast<const uint32_t *>(c.state + (size_t)e0 * c.env_stride);
-        int j = 0, w = lane;
-        while (w >= wps) { w -= wps; j++; }
-        for (int idx = lane; idx < total; idx += 32) {
-            *reinterpret_cast<uint32_t *>(smem + t.off_blk + (size_t)j * t.blk_stride + 4 * w) = src[idx];
-            w += 32;
-            while (w >= wps) { w -= wps; j++; }
+        for (int j = 0; j < nsc; j++) {
+            uint32_t *dst = reinterpret_cast<uint32_t *>(smem + t.off_blk + (size_t)j * t.blk_stride);
+#pragma unroll 4
+            for (int w = lane; w < wps; w += 32) dst[w] = src[j * wps + w];
         }
         __syncwarp();
     }
     __device__ __forceinline__ void store_blocks(int e0) {
         __syncwarp();
-        const int nsc = min(SPW, c.E - e0), wps = c.env_stride >> 2, total = nsc * wps;
+        const int nsc = min(SPW, c.E - e0), wps = c.env_stride >> 2;
         uint32_t *dst = reinterpret_cast<uint32_t *>(c.state + (size_t)e0 * c.env_stride);
-        int j = 0, w = lane;
-        while (w >= wps) { w -= wps; j++; }
-        for (int idx = lane; idx < total; idx += 32) {
-            dst[idx] = *reinterpret_cast<const uint32_t *>(smem + t.off_blk + (size_t)j * t.blk_stride + 4 * w);
-            w += 32;
-            while (w >= wps) { w -= wps; j++; }
+        for (int j = 0; j < nsc; j++) {
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(smem + t.off_blk + (size_t)j * t.blk_stride);
+#pragma unroll 4
+            for (int w = lane; w < wps; w += 32) dst[j * wps + w] = src[w];
         }
     }
     // blocks are only 4-byte aligned in shared memory (odd word stride): the header is accessed as
@@ -456,33 +532,30 @@ struct LaneScene {
         const uint64_t *zr = reinterpret_cast<const uint64_t *>(smem + t.off_zero);
         const int a = lane_monotone<NW>(need, tab, HN, om ? occ : zr, om ? occm : zr, loaded, sx, sy, tx, ty, l);
         if (need && a >= 0) { action = a; len = l; need = false; }
+        // the rest needs the level-synchronous BFS: warp-cooperative, one scene at a time
         unsigned pend = __ballot_sync(FULL, need);
-        while (pend) {  // warp-cooperative BFS, one scene at a time
+        if (!pend) return;
+#ifdef AGV_LANES_PROF
+        const long long pb0_ = clock64();
+        struct Acc { long long &a, &n; long long t0; __device__ ~Acc() { a += clock64() - t0; n++; } } acc_{pbfs, pnb, pb0_};
+#endif
+        const unsigned pk = (unsigned)sx | ((unsigned)sy << 7) | ((unsigned)tx << 14) | ((unsigned)ty << 21) |
+                            ((unsigned)loaded << 28) | (om ? (1u << 29) : 0u);
+        if (NWK > 0) {  // handed to the worker warps of the CTA
+            LaneQueue *q = queue();
+            wait_done();
+            const int slot = __popc(pend & ((1u << lane) - 1u));
+            if (need) q->req[slot] = make_uint4(pk, (unsigned)lane, 0u, 0u);
+            post(Q_BFS, __popc(pend), 0, 0);
+            wait_done();
+            if (need) { const unsigned r = q->res[slot]; action = (int)(r & 0xFFu); len = (int)(r >> 8); }
+            return;
+        }
+        while (pend) {
             const int j = __ffs(pend) - 1;
             pend &= pend - 1;
-            const unsigned pk = (unsigned)sx | ((unsigned)sy << 7) | ((unsigned)tx << 14) | ((unsigned)ty << 21) |
-                                ((unsigned)loaded << 28) | (om ? (1u << 29) : 0u);
-            const unsigned q = __shfl_sync(FULL, pk, j);
-            const int jsx = q & 127, jsy = (q >> 7) & 127, jtx = (q >> 14) & 127, jty = (q >> 21) & 127;
-            const int jl = (q >> 28) & 1;
-            const uint64_t jom = (q >> 29) & 1 ? ~0ull : 0ull;
-            const uint64_t *oj = occ_of(j), *bj = tab + jl * HN;
-            Row<NW> v[RPL];
-#pragma unroll
-            for (int s = 0; s < RPL; s++) {
-                const int r = lane * RPL + s;
-                v[s] = rzero<NW>();
-                if (r < c.H) {
-#pragma unroll
-                    for (int i = 0; i < NW; i++) {
-                        uint64_t b = bj[r * NW + i];
-                        if (r == jty && i == (jtx >> 6)) b |= 1ull << (jtx & 63);
-                        v[s].w[i] = b & ~(oj[r * NW + i] & jom);
-                    }
-                }
-            }
             int bl = 0;
-            const int ba = warp_bfs<NW, RPL>(v, jsx, jsy, jtx, jty, c.H, c.W, lane, bl);
+            const int ba = coop_bfs<NW, RPL>(__shfl_sync(FULL, pk, j), tab, HN, occ_of(j), c.H, c.W, lane, bl);
             if (lane == j) { action = ba; len = bl; }
         }
     }
@@ -490,15 +563,25 @@ struct LaneScene {
     // ---- observation of AGV `a` (index i) of the lanes with `want`, written to base + rec * R
     // matrix (b): StateManager.create_path_matrix, StateManager.py:43-61
     template <int OBS>
-    __device__ __forceinline__ void encode(bool want, const Agv &a, int i, uint16_t *base) {
+    __device__ __forceinline__ void encode(bool want, const Agv &a, int i, int which) {
         bool shared = false;
         if (want && overlap) shared = other_at(i, a.x | (a.y << 8));
         unsigned pend = __ballot_sync(FULL, want);
+        if (!pend) return;
+        uint16_t *base = which ? t.next_obs : t.obs;
+        const int slot = __popc(pend & ((1u << lane) - 1u));
         if (OBS == OBS_CLIP && c.K == 7) {
-            // lane-local window extraction, then 32 lanes expand and store one record at a time
+            // lane-local window extraction; the expansion to 147 bf16 and the stores are warp-wide
             uint64_t wm = 0ull;
             if (want) wm = lane_window7<NW>(tab + a.loaded * HN, occ, c.H, a.x - 1, a.y - 1, a.tx - 1, a.ty - 1, shared);
             const int tpos = (max(-3, min(3, a.ty - a.y)) + 3) * 7 + max(-3, min(3, a.tx - a.x)) + 3;
+            if (NWK > 0) {  // fire and forget: the request carries everything the record needs
+                LaneQueue *q = queue();
+                wait_done();
+                if (want) q->req[slot] = make_uint4((unsigned)wm, (unsigned)(wm >> 32), (unsigned)tpos, (unsigned)lane);
+                post(Q_ENC7, __popc(pend), i, which);
+                return;
+            }
             while (pend) {
                 const int j = __ffs(pend) - 1;
                 pend &= pend - 1;
@@ -510,41 +593,91 @@ struct LaneScene {
         }
         const unsigned pk = (unsigned)a.x | ((unsigned)a.y << 8) | ((unsigned)a.tx << 16) | ((unsigned)a.ty << 24);
         const unsigned fl = (unsigned)a.loaded | (shared ? 2u : 0u);
+        if (NWK > 0) {  // the workers read this scene's occupancy rows: wait before the move is applied
+            LaneQueue *q = queue();
+            wait_done();
+            if (want) q->req[slot] = make_uint4(pk, fl, 0u, (unsigned)lane);
+            post(Q_ENCG, __popc(pend), i, which);
+            wait_done();
+            return;
+        }
         while (pend) {
             const int j = __ffs(pend) - 1;
             pend &= pend - 1;
             const unsigned q = __shfl_sync(FULL, pk, j), f = __shfl_sync(FULL, fl, j);
-            const int jx = q & 255, jy = (q >> 8) & 255, jtx = (q >> 16) & 255, jty = q >> 24;
-            const int jl = f & 1;
-            const bool jshared = f & 2;
-            const uint64_t *oj = occ_of(j), *bj = tab + jl * HN;
-            for (int r = lane; r < c.H; r += 32) {
-#pragma unroll
-                for (int w = 0; w < NW; w++) {
-                    uint64_t b = bj[r * NW + w], o = oj[r * NW + w];
-                    if (r == jy - 1 && w == ((jx - 1) >> 6)) {
-                        b |= 1ull << ((jx - 1) & 63);
-                        if (!jshared) o &= ~(1ull << ((jx - 1) & 63));
-                    }
-                    if (r == jty - 1 && w == ((jtx - 1) >> 6)) b |= 1ull << ((jtx - 1) & 63);
-                    vrow[r * NW + w] = b & ~o;
-                }
-            }
-            __syncwarp();
             uint16_t *dst = base + ((size_t)(e - lane + j) * c.N + i) * t.rec_elems;
-            if (OBS == OBS_CLIP) coop_encode_clip<NW>(dst, vrow, c.H, c.W, c.K, jx, jy, jtx, jty, lane);
-            else coop_encode_full<NW>(dst, vrow, c.H, c.W, jx, jy, jtx, jty, lane);
-            __syncwarp();
+            coop_encode<NW, OBS>(q, f, tab, HN, occ_of(j), vrow, c.H, c.W, c.K, dst, lane);
         }
+    }
+
+    // ---- request queue to the worker warps (NWK > 0)
+    __device__ __forceinline__ LaneQueue *queue() const { return reinterpret_cast<LaneQueue *>(smem + t.off_queue); }
+    __device__ __forceinline__ void wait_done() {
+        if (inflight) { named_bar_sync(BAR_DONE, 32 * (1 + NWK)); inflight = false; }
+    }
+    __device__ __forceinline__ void post(int kind, int n, int i, int which) {
+        if (lane == 0) {
+            LaneQueue *q = queue();
+            q->kind = kind; q->n = n; q->i = i; q->which = which;
+        }
+        __threadfence_block();
+        named_bar_arrive(BAR_GO, 32 * (1 + NWK));
+        inflight = true;
     }
 };
 
+// worker warp of a lane-per-scene CTA: serves BFS and record-expansion requests
+template <int NW, int RPL, int OBS, int SPW, int NWK>
+__device__ __forceinline__ void lane_worker(const DevCfg &c, const LaneArgs &t, uint8_t *smem, int wid) {
+    const int lane = threadIdx.x & 31;
+    const int e0 = blockIdx.x * SPW, HN = c.H * NW;
+    LaneQueue *q = reinterpret_cast<LaneQueue *>(smem + t.off_queue);
+    const uint64_t *tab = reinterpret_cast<const uint64_t *>(smem + t.off_tab);
+    const uint64_t *occ0 = reinterpret_cast<const uint64_t *>(smem + t.off_occ);
+    uint64_t *vrow = reinterpret_cast<uint64_t *>(smem + t.off_vrow) + (size_t)(wid + 1) * HN;
+    for (;;) {
+        named_bar_sync(BAR_GO, 32 * (1 + NWK));
+        const int kind = q->kind, n = q->n;
+        if (kind == Q_EXIT) return;
+        if (kind == Q_BFS) {
+            for (int r = wid; r < n; r += NWK) {
+                const uint4 rq = q->req[r];
+                int bl = 0;
+                const int ba = coop_bfs<NW, RPL>(rq.x, tab, HN, occ0 + (size_t)rq.y * t.occ_stride, c.H, c.W, lane, bl);
+                if (lane == 0) q->res[r] = (unsigned)ba | ((unsigned)bl << 8);
+            }
+        } else {
+            uint16_t *base = q->which ? t.next_obs : t.obs;
+            const int i = q->i;
+            for (int r = wid; r < n; r += NWK) {
+                const uint4 rq = q->req[r];
+                uint16_t *dst = base + ((size_t)(e0 + (int)rq.w) * c.N + i) * t.rec_elems;
+                if (kind == Q_ENC7) expand_clip7(dst, (uint64_t)rq.x | ((uint64_t)rq.y << 32), (int)rq.z, lane);
+                else coop_encode<NW, OBS>(rq.x, rq.y, tab, HN, occ0 + (size_t)rq.w * t.occ_stride, vrow, c.H, c.W, c.K, dst, lane);
+            }
+        }
+        __threadfence_block();
+        named_bar_arrive(BAR_DONE, 32 * (1 + NWK));
+    }
+}
+
+#ifdef AGV_LANES_PROF
+#define PROF_DECL long long pt_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long pc_ = clock64();
+#define PROF(k) { const long long n_ = clock64(); pt_[k] += n_ - pc_; pc_ = n_; }
+#define PROF_FLUSH pt_[8] = ws.pbfs; pt_[9] = ws.pnb; pt_[10] = n_max; if (lane == 0) { { long long tot_ = 0; for (int k_ = 0; k_ < 8; k_++) tot_ += pt_[k_]; atomicMax(c.counters + 16, (unsigned long long)tot_); atomicMax(c.counters + 17, (unsigned long long)pt_[3]); atomicMax(c.counters + 18, (unsigned long long)ws.pbfs); atomicMax(c.counters + 19, (unsigned long long)ws.pnb);} for (int k_ = 0; k_ < 12; k_++) atomicAdd(c.counters + 3 + k_, (unsigned long long)pt_[k_]); atomicAdd(c.counters + 15, 1ull); }
+#else
+#define PROF_DECL
+#define PROF(k)
+#define PROF_FLUSH
+#endif
+
 // One pass of Scene.run_mode's loop body (Scene.py:111-164) for SPW scenes per warp.
-template <int NW, int RPL, int OBS, bool SHAPED, int SPW>
+template <int NW, int RPL, int OBS, bool SHAPED, int SPW, int NWK>
 __device__ __forceinline__ void tick_lanes(const DevCfg &c, const LaneArgs &t, uint8_t *smem) {
     const int lane = threadIdx.x & 31;
     const int e0 = blockIdx.x * SPW;
-    LaneScene<NW, RPL, SPW> ws(c, t, smem, lane, e0);
+    LaneScene<NW, RPL, SPW, NWK> ws(c, t, smem, lane, e0);
+    PROF_DECL
     ws.load_tables();
     ws.load_blocks(e0);
     const int N = c.N;
@@ -577,6 +710,7 @@ __device__ __forceinline__ void tick_lanes(const DevCfg &c, const LaneArgs &t, u
     const uint64_t om_a = N > 1 ? ~0ull : 0ull;  // matrix (a) blocks the explorers only when group size > 1
     const bool want_obs = OBS != OBS_NONE && t.obs != nullptr, want_next = OBS != OBS_NONE && t.next_obs != nullptr;
 
+    PROF(0)
     for (int i = 0; i < n_max; i++) {
         bool act = false;
         if (i < n_loop && !ws.over) {
@@ -591,7 +725,9 @@ __device__ __forceinline__ void tick_lanes(const DevCfg &c, const LaneArgs &t, u
             a = ws.load_agv(i);
             if (t.policy == POLICY_GIVEN && t.action) given = (int)t.action[(size_t)ws.e * N + i];
         }
-        if (want_obs) ws.template encode<OBS>(act, a, i, t.obs);
+        PROF(1)
+        if (want_obs) ws.template encode<OBS>(act, a, i, 0);
+        PROF(2)
         // ---- action
         const bool guided = (t.policy == POLICY_GUIDED) || (t.policy == POLICY_GIVEN && given < 0);
         const bool pol_a = !guided && t.policy == POLICY_ASTAR;
@@ -606,6 +742,7 @@ __device__ __forceinline__ void tick_lanes(const DevCfg &c, const LaneArgs &t, u
             __syncwarp();
             if (guard) ws.occ_clear(0, 0);
         }
+        PROF(3)
         if (act && !guided && !pol_a && action > A_STOP) { ws.cnt_bad++; action = A_STOP; }
         // ---- Explorer.check_action, Explorer.py:151-208
         const int dx = (action == A_RIGHT) - (action == A_LEFT);
@@ -669,8 +806,12 @@ __device__ __forceinline__ void tick_lanes(const DevCfg &c, const LaneArgs &t, u
             if (t.slen) t.slen[rec] = (uint16_t)slen;
         }
         __syncwarp();
-        if (want_next) ws.template encode<OBS>(act, a, i, t.next_obs);  // store_info's create_state (Scene.py:156)
+        PROF(4)
+        if (want_next) ws.template encode<OBS>(act, a, i, 1);
+        PROF(5)  // store_info's create_state (Scene.py:156)
     }
+    PROF(6)
+    if (NWK > 0) { ws.wait_done(); ws.post(Q_EXIT, 0, 0, 0); }
     if (live && !ws.over) ws.spawn();
     if (ws.has) ws.regs_to_hdr();
     {
@@ -683,6 +824,8 @@ __device__ __forceinline__ void tick_lanes(const DevCfg &c, const LaneArgs &t, u
         }
     }
     ws.store_blocks(e0);
+    PROF(7)
+    PROF_FLUSH
 }
 
 }  // namespace agv
