@@ -275,31 +275,47 @@ __device__ __forceinline__ int warp_bfs(const Row<NW> (&valid)[RPL], int sx, int
         }
         // (the up to 3 remaining hit-free levels run in phase 2: one loop body less to fetch)
     }
-    // Phase 2: hit test every level.
+    // Phase 2: blocks of AGV_BFS_UNROLL levels with a lane-local hit flag and ONE vote per block
+    // (a vote + branch per level made every level wait for the vote's latency); the block in which
+    // the frontier first touches a start neighbour is replayed level by level from its saved start.
     for (;;) {
+        Row<NW> f0[RPL], av0[RPL];
+#pragma unroll
+        for (int s = 0; s < RPL; s++) { f0[s] = f[s]; av0[s] = av[s]; }
+        bool h = false;
 #pragma unroll
         for (int u = 0; u < AGV_BFS_UNROLL; u++) {
-            bool hit = false;
 #pragma unroll
-            for (int s = 0; s < RPL; s++) hit |= rany(rand_(f[s], nb[s]));
-            if (__any_sync(FULL, hit)) {
-                unsigned code = 0;
-                if (sx + 1 < W && test_bit_local<NW, RPL>(f, sy, sx + 1, lane)) code |= 1u;
-                if (sy + 1 < H && test_bit_local<NW, RPL>(f, sy + 1, sx, lane)) code |= 2u;
-                if (sy - 1 >= 0 && test_bit_local<NW, RPL>(f, sy - 1, sx, lane)) code |= 4u;
-                if (sx - 1 >= 0 && test_bit_local<NW, RPL>(f, sy, sx - 1, lane)) code |= 8u;
-                code = __reduce_or_sync(FULL, code);
-                len = level + 1;
-                if (code & 1u) return A_RIGHT;
-                if (code & 2u) return A_DOWN;
-                if (code & 4u) return A_UP;
-                return A_LEFT;
-            }
+            for (int s = 0; s < RPL; s++) h |= rany(rand_(f[s], nb[s]));
             bfs_expand<NW, RPL>(f, av, m_up, m_dn);
-            ++level;
         }
-        // the frontier-empty test (target unreachable) is amortised over 4 levels: an empty
-        // frontier stays empty, so at most 3 extra no-op levels are expanded
+        if (__any_sync(FULL, h)) {
+#pragma unroll
+            for (int s = 0; s < RPL; s++) { f[s] = f0[s]; av[s] = av0[s]; }
+#pragma unroll 1
+            for (;;) {
+                bool hit = false;
+#pragma unroll
+                for (int s = 0; s < RPL; s++) hit |= rany(rand_(f[s], nb[s]));
+                if (__any_sync(FULL, hit)) {
+                    unsigned code = 0;
+                    if (sx + 1 < W && test_bit_local<NW, RPL>(f, sy, sx + 1, lane)) code |= 1u;
+                    if (sy + 1 < H && test_bit_local<NW, RPL>(f, sy + 1, sx, lane)) code |= 2u;
+                    if (sy - 1 >= 0 && test_bit_local<NW, RPL>(f, sy - 1, sx, lane)) code |= 4u;
+                    if (sx - 1 >= 0 && test_bit_local<NW, RPL>(f, sy, sx - 1, lane)) code |= 8u;
+                    code = __reduce_or_sync(FULL, code);
+                    len = level + 1;
+                    if (code & 1u) return A_RIGHT;
+                    if (code & 2u) return A_DOWN;
+                    if (code & 4u) return A_UP;
+                    return A_LEFT;
+                }
+                bfs_expand<NW, RPL>(f, av, m_up, m_dn);
+                ++level;
+            }
+        }
+        level += AGV_BFS_UNROLL;
+        // frontier-empty test (target unreachable) once per block: an empty frontier stays empty
         bool ne = false;
 #pragma unroll
         for (int s = 0; s < RPL; s++) ne |= rany(f[s]);

@@ -12,7 +12,7 @@
 
 namespace agv {
 
-int lanes_tick(const DevCfg &dc, int NW, int RPL, const LaneArgs &t, cudaStream_t st);  // agv_lanes.cu
+int lanes_tick(const DevCfg &dc, int NW, int RPL, const LaneArgs &t, cudaStream_t st, int allow_async);  // agv_lanes.cu
 
 static std::atomic<uint64_t> g_launches{0};
 static int g_last_cuda = 0;
@@ -390,11 +390,14 @@ static int warps_per_cta() {
     return v;
 }
 
-// fused-tick implementation: "lanes" (lane-per-scene, agv_lanes.cuh; default) or "warp"
-// (warp-per-scene k_tick).  Both are bit-identical; AGV_TICK_IMPL selects for A/B runs and tests.
-static bool tick_impl_lanes() {
+// fused-tick implementation: "async" (lane-per-scene with decoupled lanes, agv_async.cuh; the
+// default where it applies), "lanes" (lane-per-scene in lock step, agv_lanes.cuh) or "warp"
+// (warp-per-scene k_tick).  All are bit-identical; AGV_TICK_IMPL selects for A/B runs and tests.
+static int tick_impl() {  // 0 warp, 1 lanes, 2 async
     const char *e = getenv("AGV_TICK_IMPL");
-    return !(e && strcmp(e, "warp") == 0);
+    if (e && strcmp(e, "warp") == 0) return 0;
+    if (e && strcmp(e, "lanes") == 0) return 1;
+    return 2;
 }
 
 template <typename K, typename... Args>
@@ -542,12 +545,12 @@ int agv_tick(AgvHandle *h, int32_t proto, int32_t policy, int32_t obs_kind, cons
     t.obs = (uint16_t *)obs_dev; t.next_obs = (uint16_t *)next_obs_dev;
     const int N = h->cfg.N;
     t.rec_elems = obs_elems(h, t.obs_kind);
-    if (tick_impl_lanes()) {
+    if (tick_impl() > 0) {
         LaneArgs la; memset(&la, 0, sizeof(la));
         la.proto = t.proto; la.policy = t.policy; la.obs_kind = t.obs_kind;
         la.action = t.action; la.act_out = t.act_out; la.reward = t.reward; la.done = t.done;
         la.plen = t.plen; la.slen = t.slen; la.obs = t.obs; la.next_obs = t.next_obs; la.rec_elems = t.rec_elems;
-        const int rc = lanes_tick(h->dc, h->NW, h->RPL, la, (cudaStream_t)stream);
+        const int rc = lanes_tick(h->dc, h->NW, h->RPL, la, (cudaStream_t)stream, tick_impl() == 2);
         if (rc != AGV_E_UNSUPPORTED) return rc;  // scenes too large for a lane-per-scene warp: warp-per-scene path
     }
     t.group = 1;
@@ -733,7 +736,7 @@ int agv_read_counters(AgvHandle *h, uint64_t out[3], void *stream) {
     CUDA_TRY(cudaStreamSynchronize(st));
     if (getenv("AGV_PROF_DUMP")) {
         fprintf(stderr, "agv prof:");
-        for (int i = 3; i < 20; i++) fprintf(stderr, " %llu", tmp[i]);
+        for (int i = 3; i < 28; i++) fprintf(stderr, " %llu", tmp[i]);
         fprintf(stderr, "\n");
     }
     out[0] = tmp[0]; out[1] = tmp[1]; out[2] = tmp[2];

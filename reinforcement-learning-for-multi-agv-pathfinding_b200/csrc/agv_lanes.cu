@@ -1,6 +1,6 @@
 // agv_lanes.cu -- kernels + launcher of the lane-per-scene fused tick (agv_lanes.cuh).
 // sm_100a only.  Called from agv_tick (agv_kernels.cu).
-#include "agv_lanes.cuh"
+#include "agv_async.cuh"
 
 #include <cstdlib>
 
@@ -20,10 +20,17 @@ __global__ void __launch_bounds__(32 * (1 + NWK)) k_tick_lanes(const DevCfg c, c
     else tick_lanes<NW, RPL, OBS, SHAPED, SPW, NWK>(c, t, lane_smem);
 }
 
+// decoupled lanes: scene warp + NB BFS workers (+ the record writer for OBS_CLIP)
+template <int NW, int RPL, int OBS, int SPW, int NB>
+__global__ void __launch_bounds__(32 * (1 + NB + (OBS == OBS_CLIP ? 1 : 0))) k_tick_async(const DevCfg c, const LaneArgs t) {
+    extern __shared__ __align__(16) uint8_t lane_smem[];
+    async_cta<NW, RPL, OBS, SPW, NB>(c, t, lane_smem);
+}
+
 static inline int align8(int x) { return (x + 7) & ~7; }
 
-template <int NW, int RPL, int OBS, bool SHAPED, int SPW, int NWK>
-static int launch_lanes(const DevCfg &dc, LaneArgs t, cudaStream_t st) {
+template <int NW, int SPW>
+static int plan_lanes(const DevCfg &dc, LaneArgs &t, int n_vrow, int queue_bytes) {
     const int HN = dc.H * NW;
     int off = 0;
     t.off_tab = off; off += 4 * HN * 8;
@@ -32,9 +39,39 @@ static int launch_lanes(const DevCfg &dc, LaneArgs t, cudaStream_t st) {
     t.occ_stride = HN | 1;
     t.off_occ = off; off += SPW * t.occ_stride * 8;
     t.off_occm = off; off += SPW * t.occ_stride * 8;
-    t.off_vrow = off; off += (1 + NWK) * HN * 8;
+    t.off_vrow = off; off += n_vrow * HN * 8;
     t.off_zero = off; off += HN * 8;
-    t.off_queue = (off + 15) & ~15; off = t.off_queue + (int)sizeof(LaneQueue);
+    t.off_queue = (off + 15) & ~15; off = t.off_queue + queue_bytes;
+    return off;
+}
+
+template <int NW, int RPL, int OBS, int SPW, int NB>
+static int launch_async(const DevCfg &dc, LaneArgs t, cudaStream_t st) {
+    const int smem = plan_lanes<NW, SPW>(dc, t, 1, (int)sizeof(AsyncShared));
+    auto kern = k_tick_async<NW, RPL, OBS, SPW, NB>;
+    if (smem > 227 * 1024) return -4;  // AGV_E_UNSUPPORTED
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) { note_cuda_error((int)e); return -2; }
+    }
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    const int ctas = (dc.E + SPW - 1) / SPW;
+    kern<<<ctas, 32 * (1 + NB + (OBS == OBS_CLIP ? 1 : 0)), smem, st>>>(dc, t);
+    note_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { note_cuda_error((int)e); return -2; }
+    return 0;
+}
+
+template <int NW, int RPL, int SPW, int NB>
+static int dispatch_async(const DevCfg &dc, const LaneArgs &t, cudaStream_t st) {
+    if (t.obs_kind == OBS_CLIP) return launch_async<NW, RPL, OBS_CLIP, SPW, NB>(dc, t, st);
+    return launch_async<NW, RPL, OBS_NONE, SPW, NB>(dc, t, st);
+}
+
+template <int NW, int RPL, int OBS, bool SHAPED, int SPW, int NWK>
+static int launch_lanes(const DevCfg &dc, LaneArgs t, cudaStream_t st) {
+    const int off = plan_lanes<NW, SPW>(dc, t, 1 + NWK, (int)sizeof(LaneQueue));
     auto kern = k_tick_lanes<NW, RPL, OBS, SHAPED, SPW, NWK>;
     if (off > 227 * 1024) return -4;  // AGV_E_UNSUPPORTED
     if (off > 48 * 1024) {
@@ -60,7 +97,27 @@ static int dispatch_obs(const DevCfg &dc, const LaneArgs &t, cudaStream_t st) {
 
 // scenes per warp (SPW) and worker warps per CTA (NWK); AGV_LANES_SPW / AGV_LANES_NWK select among
 // the variants compiled into tuning builds (-DAGV_LANES_TUNE)
-int lanes_tick(const DevCfg &dc, int NW, int RPL, const LaneArgs &t, cudaStream_t st) {
+int lanes_tick(const DevCfg &dc, int NW, int RPL, const LaneArgs &t, cudaStream_t st, int allow_async) {
+    // decoupled lanes cover no-observation and 3x7x7 limited-visual ticks without the shaped reward
+    if (allow_async && !dc.shaped && (t.obs_kind == OBS_NONE || (t.obs_kind == OBS_CLIP && dc.K == 7))) {
+        if (NW == 1 && RPL == 1) return dispatch_async<1, 1, 32, 2>(dc, t, st);
+        if (NW == 1 && RPL == 2) {
+#ifdef AGV_LANES_TUNE
+            const char *e = getenv("AGV_LANES_SPW"), *w = getenv("AGV_LANES_NWK");
+            const int spw = e ? atoi(e) : 32, nb = w ? atoi(w) : 2;
+            if (spw == 32 && nb == 1) return dispatch_async<1, 2, 32, 1>(dc, t, st);
+            if (spw == 32 && nb == 3) return dispatch_async<1, 2, 32, 3>(dc, t, st);
+            if (spw == 16 && nb == 1) return dispatch_async<1, 2, 16, 1>(dc, t, st);
+            if (spw == 16 && nb == 2) return dispatch_async<1, 2, 16, 2>(dc, t, st);
+            if (spw == 8 && nb == 1) return dispatch_async<1, 2, 8, 1>(dc, t, st);
+#endif
+            return dispatch_async<1, 2, 32, 2>(dc, t, st);
+        }
+        if (NW == 1 && RPL == 4) return dispatch_async<1, 4, 32, 2>(dc, t, st);
+        if (NW == 2 && RPL == 1) return dispatch_async<2, 1, 32, 2>(dc, t, st);
+        if (NW == 2 && RPL == 2) return dispatch_async<2, 2, 32, 2>(dc, t, st);
+        return dispatch_async<2, 4, 32, 2>(dc, t, st);
+    }
     if (NW == 1 && RPL == 1) return dispatch_obs<1, 1, 32, 0>(dc, t, st);
     if (NW == 1 && RPL == 2) {
 #ifdef AGV_LANES_TUNE

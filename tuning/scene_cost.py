@@ -27,3 +27,9 @@ for t in range(3):
     print("  levels per scene: mean %.0f p50 %d p90 %d p99 %d max %d" % (per_scene.mean(), np.median(per_scene), np.percentile(per_scene, 90), np.percentile(per_scene, 99), per_scene.max()))
     print("  scenes with >=8 no-path searches: %d ; tick counter of the worst scene %d, created %d" % ((stop_search.sum(1) >= 8).sum(), hdr[per_scene.argmax(), 0], hdr[per_scene.argmax(), 4]))
     w32 = per_scene.reshape(-1, 32).sum(1); print("  per 32-scene warp levels: mean %.0f max %d" % (w32.mean(), w32.max()))
+    top = np.argsort(-per_scene)[:6]
+    for e in top:
+        print("   scene %5d: nopath %2d detour %2d (mean plen %.0f, mean manhattan %.0f) acting %d" % (
+            e, stop_search[e].sum(), detour[e].sum(), p[e][detour[e]].mean() if detour[e].any() else 0,
+            md[e][detour[e]].mean() if detour[e].any() else 0, took[e].sum()))
+    print("   all scenes: nopath %d detour %d, detour levels %d" % (stop_search.sum(), detour.sum(), p[detour].sum()))
