@@ -211,6 +211,7 @@ def main():
                     help="guided: intelligent protocol + A* guidance on matrix b (headline); "
                          "astar: Scene A_star control mode (matrix a, no episode end)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shaped", action="store_true", help="settings.Sparse_Reward shaped reward (a second path search per turn)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
     steps, warmup = max(1, args.steps), max(3, args.warmup)
@@ -264,7 +265,7 @@ def main():
     lib = pkg._lib.lib()
 
     tasks = synth_tasks(grid, E, seed=1000 + rank)
-    sc = pkg.BatchedScene(grid, E, N, tasks=tasks, P=3, auto_reset=True, device=local_rank)
+    sc = pkg.BatchedScene(grid, E, N, tasks=tasks, P=3, auto_reset=True, device=local_rank, shaped_reward=args.shaped)
     del tasks
     sc.reset()
     PROTO, POL, OBS = pkg.PROTO_INTELLIGENT, pkg.POLICY_GUIDED, pkg.OBS_CLIP

@@ -32,6 +32,9 @@ struct AsyncShared {
 };
 
 constexpr int LS_START = 0, LS_WAIT = 1, LS_HAVE = 2, LS_DONE = 3;
+#ifndef AGV_POLL_NS
+#define AGV_POLL_NS 400  // sleep between two polls of an idle worker warp (40 ns cost 10 %: the polls compete for issue slots)
+#endif
 
 template <int NW, int RPL, int SPW>
 __device__ __forceinline__ void async_bfs_worker(const DevCfg &c, const LaneArgs &t, uint8_t *smem) {
@@ -45,7 +48,7 @@ __device__ __forceinline__ void async_bfs_worker(const DevCfg &c, const LaneArgs
         unsigned m = __ballot_sync(FULL, vs[lane] == 1u);
         if (!m) {
             if (*vexit) return;
-            __nanosleep(40);
+            __nanosleep(AGV_POLL_NS);
             continue;
         }
         int j = -1;
@@ -66,7 +69,7 @@ __device__ __forceinline__ void async_bfs_worker(const DevCfg &c, const LaneArgs
 #endif
         const int ba = coop_bfs<NW, RPL>(pk, tab, HN, occ0 + (size_t)j * t.occ_stride, c.H, c.W, lane, bl);
 #ifdef AGV_LANES_PROF
-        if (lane == 0) { atomicAdd(c.counters + 3 + 8, (unsigned long long)(clock64() - b0_)); atomicAdd(c.counters + 3 + 9, 1ull); atomicAdd(c.counters + 3 + 11, (unsigned long long)bl); }
+        if (lane == 0) { const long long d_ = clock64() - b0_; atomicAdd(c.counters + 3 + 8, (unsigned long long)d_); atomicAdd(c.counters + 3 + 9, 1ull); atomicAdd(c.counters + 3 + 11, (unsigned long long)bl); if (bl == 0) { atomicAdd(c.counters + 3 + 3, (unsigned long long)d_); atomicAdd(c.counters + 3 + 4, 1ull); if (d_ < 1000) atomicAdd(c.counters + 3 + 5, 1ull); else if (d_ < 4000) atomicAdd(c.counters + 3 + 6, 1ull); else if (d_ < 12000) atomicAdd(c.counters + 3 + 7, 1ull); } }
 #endif
         if (lane == 0) {
             *reinterpret_cast<volatile unsigned *>(&sh->bfs_res[j]) = (unsigned)ba | ((unsigned)bl << 8);
@@ -89,7 +92,7 @@ __device__ __forceinline__ void async_record_writer(const LaneArgs &t, uint8_t *
                 if (*vseq == mine) return;  // the last batch is posted before the exit flag
                 continue;
             }
-            __nanosleep(40);
+            __nanosleep(AGV_POLL_NS);
             continue;
         }
         __threadfence_block();

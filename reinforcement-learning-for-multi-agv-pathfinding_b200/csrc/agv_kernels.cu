@@ -390,13 +390,20 @@ static int warps_per_cta() {
     return v;
 }
 
-// fused-tick implementation: "async" (lane-per-scene with decoupled lanes, agv_async.cuh; the
-// default where it applies), "lanes" (lane-per-scene in lock step, agv_lanes.cuh) or "warp"
-// (warp-per-scene k_tick).  All are bit-identical; AGV_TICK_IMPL selects for A/B runs and tests.
-static int tick_impl() {  // 0 warp, 1 lanes, 2 async
+// fused-tick implementation: "async" (lane-per-scene with decoupled lanes, agv_async.cuh),
+// "lanes" (lane-per-scene in lock step, agv_lanes.cuh) or "warp" (warp-per-scene k_tick).  All are
+// bit-identical (tests/test_gpu_parity.py runs every fused-tick test on each).  AGV_TICK_IMPL
+// forces one for A/B runs and tests; otherwise the measured-fastest one for the shape is taken:
+//   * full-map observations are HBM-write-bound and best written by a whole warp per scene;
+//   * maps up to 32 x 32 have short searches and few scenes per SM: warp-per-scene;
+//   * everything else runs lane-per-scene (decoupled lanes where agv_async.cuh covers it).
+static int tick_impl(const AgvHandle *h, int obs_kind) {  // 0 warp, 1 lanes, 2 async
     const char *e = getenv("AGV_TICK_IMPL");
     if (e && strcmp(e, "warp") == 0) return 0;
     if (e && strcmp(e, "lanes") == 0) return 1;
+    if (e && strcmp(e, "async") == 0) return 2;
+    if (obs_kind == AGV_OBS_FULL) return 0;
+    if (h->NW == 1 && h->RPL == 1) return 0;
     return 2;
 }
 
@@ -545,12 +552,13 @@ int agv_tick(AgvHandle *h, int32_t proto, int32_t policy, int32_t obs_kind, cons
     t.obs = (uint16_t *)obs_dev; t.next_obs = (uint16_t *)next_obs_dev;
     const int N = h->cfg.N;
     t.rec_elems = obs_elems(h, t.obs_kind);
-    if (tick_impl() > 0) {
+    const int impl = tick_impl(h, t.obs_kind);
+    if (impl > 0) {
         LaneArgs la; memset(&la, 0, sizeof(la));
         la.proto = t.proto; la.policy = t.policy; la.obs_kind = t.obs_kind;
         la.action = t.action; la.act_out = t.act_out; la.reward = t.reward; la.done = t.done;
         la.plen = t.plen; la.slen = t.slen; la.obs = t.obs; la.next_obs = t.next_obs; la.rec_elems = t.rec_elems;
-        const int rc = lanes_tick(h->dc, h->NW, h->RPL, la, (cudaStream_t)stream, tick_impl() == 2);
+        const int rc = lanes_tick(h->dc, h->NW, h->RPL, la, (cudaStream_t)stream, impl == 2);
         if (rc != AGV_E_UNSUPPORTED) return rc;  // scenes too large for a lane-per-scene warp: warp-per-scene path
     }
     t.group = 1;

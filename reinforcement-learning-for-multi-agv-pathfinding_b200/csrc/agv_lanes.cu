@@ -100,23 +100,25 @@ static int dispatch_obs(const DevCfg &dc, const LaneArgs &t, cudaStream_t st) {
 int lanes_tick(const DevCfg &dc, int NW, int RPL, const LaneArgs &t, cudaStream_t st, int allow_async) {
     // decoupled lanes cover no-observation and 3x7x7 limited-visual ticks without the shaped reward
     if (allow_async && !dc.shaped && (t.obs_kind == OBS_NONE || (t.obs_kind == OBS_CLIP && dc.K == 7))) {
-        if (NW == 1 && RPL == 1) return dispatch_async<1, 1, 32, 2>(dc, t, st);
+        if (NW == 1 && RPL == 1) return dispatch_async<1, 1, 32, 3>(dc, t, st);
         if (NW == 1 && RPL == 2) {
 #ifdef AGV_LANES_TUNE
             const char *e = getenv("AGV_LANES_SPW"), *w = getenv("AGV_LANES_NWK");
-            const int spw = e ? atoi(e) : 32, nb = w ? atoi(w) : 2;
+            const int spw = e ? atoi(e) : 32, nb = w ? atoi(w) : 3;
             if (spw == 32 && nb == 1) return dispatch_async<1, 2, 32, 1>(dc, t, st);
-            if (spw == 32 && nb == 3) return dispatch_async<1, 2, 32, 3>(dc, t, st);
+            if (spw == 32 && nb == 2) return dispatch_async<1, 2, 32, 2>(dc, t, st);
             if (spw == 16 && nb == 1) return dispatch_async<1, 2, 16, 1>(dc, t, st);
             if (spw == 16 && nb == 2) return dispatch_async<1, 2, 16, 2>(dc, t, st);
+            if (spw == 16 && nb == 3) return dispatch_async<1, 2, 16, 3>(dc, t, st);
+            if (spw == 32 && nb == 4) return dispatch_async<1, 2, 32, 4>(dc, t, st);
             if (spw == 8 && nb == 1) return dispatch_async<1, 2, 8, 1>(dc, t, st);
 #endif
-            return dispatch_async<1, 2, 32, 2>(dc, t, st);
+            return dispatch_async<1, 2, 32, 3>(dc, t, st);  // measured best at 64 x 64, 16384 scenes
         }
-        if (NW == 1 && RPL == 4) return dispatch_async<1, 4, 32, 2>(dc, t, st);
-        if (NW == 2 && RPL == 1) return dispatch_async<2, 1, 32, 2>(dc, t, st);
-        if (NW == 2 && RPL == 2) return dispatch_async<2, 2, 32, 2>(dc, t, st);
-        return dispatch_async<2, 4, 32, 2>(dc, t, st);
+        if (NW == 1 && RPL == 4) return dispatch_async<1, 4, 32, 3>(dc, t, st);
+        if (NW == 2 && RPL == 1) return dispatch_async<2, 1, 32, 3>(dc, t, st);
+        if (NW == 2 && RPL == 2) return dispatch_async<2, 2, 32, 3>(dc, t, st);
+        return dispatch_async<2, 4, 32, 3>(dc, t, st);
     }
     if (NW == 1 && RPL == 1) return dispatch_obs<1, 1, 32, 0>(dc, t, st);
     if (NW == 1 && RPL == 2) {

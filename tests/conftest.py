@@ -30,3 +30,12 @@ def golden(name):
 @pytest.fixture(scope="session")
 def pkg():
     return load_pkg()
+
+
+@pytest.fixture(params=["async", "lanes", "warp"])
+def tick_impl(request, monkeypatch):
+    """Runs a fused-tick test once per implementation of agv_tick: decoupled lanes
+    (agv_async.cuh, the default), lock-step lanes (agv_lanes.cuh) and warp-per-scene (k_tick).
+    The library reads AGV_TICK_IMPL at every call."""
+    monkeypatch.setenv("AGV_TICK_IMPL", request.param)
+    return request.param

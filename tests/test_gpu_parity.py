@@ -99,6 +99,7 @@ def test_bfs_random_vs_oracle(pkg, H, W):
             assert (dist[b] == 0xFFFF).all()
 
 
+@pytest.mark.usefixtures("tick_impl")
 @pytest.mark.parametrize("idx", range(7))
 def test_astar_trajectories_fixture(pkg, idx):
     """Scene.run_game('A_star') trajectories of the live reference"""
@@ -185,6 +186,7 @@ def test_intelligent_fixture_substep(pkg):
     assert n_turns > 6000 and n_obs > 50
 
 
+@pytest.mark.usefixtures("tick_impl")
 def test_intelligent_fixture_fused_given(pkg):
     """same recordings through the fused tick with the recorded actions"""
     eps = golden("intelligent.json")
@@ -241,6 +243,7 @@ CASES = [
 ]
 
 
+@pytest.mark.usefixtures("tick_impl")
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_fused_tick_vs_oracle(pkg, case):
     name, gridf, N, E, ticks, proto, policy, obs_kind, flags = case
@@ -269,6 +272,7 @@ def test_fused_tick_vs_oracle(pkg, case):
     sc.close()
 
 
+@pytest.mark.usefixtures("tick_impl")
 def test_fused_given_random_actions_vs_oracle(pkg):
     """random (mostly illegal) open-loop actions incl. the guided fallback (-1) and STOP"""
     grid = orc.rect_layout(4, 2, 2, 2, 2)
@@ -291,6 +295,7 @@ def test_fused_given_random_actions_vs_oracle(pkg):
         sc.close()
 
 
+@pytest.mark.usefixtures("tick_impl")
 def test_auto_reset_and_substep_equals_fused(pkg):
     """auto_reset=1: sub-step protocol (begin/encode/bfs/step/end) == fused guided tick"""
     grid = orc.README_9x9
@@ -350,6 +355,7 @@ def test_invalid_arguments(pkg):
     sc.close()
 
 
+@pytest.mark.usefixtures("tick_impl")
 @pytest.mark.parametrize("P", [1, 2, 5])
 def test_clip_window_sizes(pkg, P):
     """limited visual with padding sizes other than the default 3 (K = 3, 5, 11)"""
@@ -370,6 +376,7 @@ def test_clip_window_sizes(pkg, P):
     sc.close()
 
 
+@pytest.mark.usefixtures("tick_impl")
 def test_edge_scenes(pkg):
     """no tasks at all, one task for many AGVs, a 1-row corridor, an early max_steps ending"""
     # T = 0: AGV 0 is created idle, task_finished is raised at creation, the next tick returns
@@ -406,6 +413,7 @@ def test_edge_scenes(pkg):
     sc.close()
 
 
+@pytest.mark.usefixtures("tick_impl")
 def test_injected_overlapping_state(pkg):
     """agv_set_state with two created AGVs on one cell (reachable in the reference through the
     A_star protocol with hand-fed actions): the slow-path ballots must agree with the oracle"""
@@ -465,6 +473,7 @@ def test_c_abi_from_plain_c(pkg, tmp_path):
     assert out[-1].startswith("turns %d " % turns)
 
 
+@pytest.mark.usefixtures("tick_impl")
 def test_output_buffers_are_not_overrun(pkg):
     """compute-sanitizer is closed on this pool, so out-of-bounds stores are hunted with guard
     bands: every output tensor of agv_tick / agv_encode is a window into a larger buffer filled
