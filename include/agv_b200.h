@@ -203,6 +203,9 @@ int agv_last_cuda_error(void);
 /* number of kernel launches issued through this library since load (for bench.py) */
 uint64_t agv_launch_count(void);
 const char *agv_version(void);
+/* name of the kernel the last agv_tick / agv_tick_host call launched (three bit-identical
+ * implementations exist; the library picks by shape, AGV_TICK_IMPL=async|lanes|warp forces one) */
+const char *agv_last_tick_kernel(void);
 
 #ifdef __cplusplus
 }

@@ -55,6 +55,7 @@ SYMBOLS = {
     "agv_last_cuda_error": (C.c_int, []),
     "agv_launch_count": (C.c_uint64, []),
     "agv_version": (C.c_char_p, []),
+    "agv_last_tick_kernel": (C.c_char_p, []),
 }
 
 _lib = None

@@ -15,6 +15,7 @@ namespace agv {
 int lanes_tick(const DevCfg &dc, int NW, int RPL, const LaneArgs &t, cudaStream_t st, int allow_async);  // agv_lanes.cu
 
 static std::atomic<uint64_t> g_launches{0};
+static const char *g_tick_kernel = "none";
 static int g_last_cuda = 0;
 
 struct TickArgs {
@@ -559,8 +560,14 @@ int agv_tick(AgvHandle *h, int32_t proto, int32_t policy, int32_t obs_kind, cons
         la.action = t.action; la.act_out = t.act_out; la.reward = t.reward; la.done = t.done;
         la.plen = t.plen; la.slen = t.slen; la.obs = t.obs; la.next_obs = t.next_obs; la.rec_elems = t.rec_elems;
         const int rc = lanes_tick(h->dc, h->NW, h->RPL, la, (cudaStream_t)stream, impl == 2);
-        if (rc != AGV_E_UNSUPPORTED) return rc;  // scenes too large for a lane-per-scene warp: warp-per-scene path
+        if (rc != AGV_E_UNSUPPORTED) {
+            const bool as = impl == 2 && !h->dc.shaped && (t.obs_kind == AGV_OBS_NONE || (t.obs_kind == AGV_OBS_CLIP && h->dc.K == 7));
+            g_tick_kernel = as ? "k_tick_async (lane-per-scene, decoupled lanes + BFS worker warps)"
+                               : "k_tick_lanes (lane-per-scene, lock step)";
+            return rc;
+        }  // scenes too large for a lane-per-scene warp: warp-per-scene path
     }
+    g_tick_kernel = "k_tick (warp-per-scene)";
     t.group = 1;
     if (t.obs_kind == AGV_OBS_CLIP) {
         const int rb = t.rec_elems * 2;
@@ -790,7 +797,8 @@ const char *agv_strerror(int status) {
 
 int agv_last_cuda_error(void) { return g_last_cuda; }
 uint64_t agv_launch_count(void) { return g_launches.load(); }
-const char *agv_version(void) { return "agv_b200 0.1 (sm_100a)"; }
+const char *agv_version(void) { return "agv_b200 0.2 (sm_100a)"; }
+const char *agv_last_tick_kernel(void) { return g_tick_kernel; }
 
 }  // extern "C"
 
