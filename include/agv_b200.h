@@ -118,10 +118,15 @@ int agv_tick(AgvHandle *h, int32_t proto, int32_t policy, int32_t obs_kind,
 
 /* Same, with HOST buffers for the per-step inputs and results (pinned memory):
  * copies action_host -> device, runs the tick, copies act/reward/done back.
- * obs stay on the device (they feed the CNN).  Asynchronous on `stream`. */
+ * obs stay on the device (they feed the CNN).  The copy-back runs on an internal
+ * stream from double-buffered device results, so it overlaps the next call's tick;
+ * agv_tick_host_join makes `stream` wait for every outstanding copy-back -- after it,
+ * anything ordered on `stream` (an event, a synchronize) covers the host results.
+ * Callers that need step k's results before issuing step k+1 join after each call. */
 int agv_tick_host(AgvHandle *h, int32_t proto, int32_t policy, int32_t obs_kind,
                   const int8_t *action_host, int8_t *act_out_host, float *reward_host, uint8_t *done_host,
                   void *obs_dev, void *next_obs_dev, void *stream);
+int agv_tick_host_join(AgvHandle *h, void *stream);
 
 /* ---- sub-step protocol (NN in the loop) -------------------------------------
  * The callback protocol of Scene.py:144-158 split into tensor calls per AGV index k:

@@ -34,6 +34,7 @@ SYMBOLS = {
     "agv_reset": (C.c_int, [_vp, _vp, _vp]),
     "agv_tick": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "agv_tick_host": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "agv_tick_host_join": (C.c_int, [_vp, _vp]),
     "agv_begin_tick": (C.c_int, [_vp, _vp]),
     "agv_encode": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "agv_bfs_action": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp]),

@@ -126,8 +126,10 @@ class BatchedScene:
                                   _ptr(o.get("next_obs")), self._stream()), "agv_tick")
         return o
 
-    def tick_host(self, proto, policy, obs_kind=L.OBS_NONE, actions_host=None, want_next=False):
-        """Same through HOST (pinned) buffers for actions in and act/reward/done out."""
+    def tick_host(self, proto, policy, obs_kind=L.OBS_NONE, actions_host=None, want_next=False, join=True):
+        """Same through HOST (pinned) buffers for actions in and act/reward/done out.  The copy-back
+        runs on the library's own stream and overlaps the next tick; with `join` (default) the
+        caller's stream waits for it right away, otherwise call host_join() before reading."""
         E, N = self.E, self.N
         hb = self._buf.setdefault("host", {})
         if not hb:
@@ -147,7 +149,13 @@ class BatchedScene:
         L.check(self.lib.agv_tick_host(self._h, proto, policy, obs_kind, _ptr(ah), _ptr(hb["act"]),
                                        _ptr(hb["reward"]), _ptr(hb["done"]), _ptr(obs), _ptr(nxt), self._stream()),
                 "agv_tick_host")
+        if join:
+            self.host_join()
         return {"act": hb["act"], "reward": hb["reward"], "done": hb["done"], "obs": obs, "next_obs": nxt}
+
+    def host_join(self):
+        """The current stream waits for the outstanding copy-backs of tick_host."""
+        L.check(self.lib.agv_tick_host_join(self._h, self._stream()), "agv_tick_host_join")
 
     def collect_expert(self, replay, n_ticks: int, obs_kind=L.OBS_CLIP):
         """Expert-mode rollout collection (ExpertManager.create_data_by_self, batched): `n_ticks`

@@ -517,3 +517,34 @@ def test_output_buffers_are_not_overrun(pkg):
             assert (buf[:G] == fill).all() and (buf[-G:] == fill).all(), (name, E, N, kind)
         assert set(out["obs"].float().unique().tolist()) <= {0.0, 1.0, 7.0}
         sc.close()
+
+
+def test_tick_host_equals_tick(pkg):
+    """agv_tick_host (pinned host buffers, overlapped copy-back) returns what agv_tick returns"""
+    import torch
+    grid = orc.rect_layout(4, 2, 2, 2, 2)
+    E, N = 64, 4
+    tasks = np.array([orc.make_tasks(grid, random.Random(100 + s)) for s in range(E)], dtype=np.uint8)
+    a = pkg.BatchedScene(grid, E, N, tasks=tasks, auto_reset=True)
+    b = pkg.BatchedScene(grid, E, N, tasks=tasks, auto_reset=True)
+    a.reset(); b.reset()
+    rng = np.random.default_rng(5)
+    hist = []
+    for t in range(40):
+        acts = rng.integers(-1, 5, size=(E, N)).astype(np.int8)
+        o = a.tick(pkg.PROTO_INTELLIGENT, pkg.POLICY_GIVEN, pkg.OBS_CLIP, actions=acts)
+        ah = torch.from_numpy(acts).pin_memory()
+        # join=False on odd steps: the result is only read after the explicit join below
+        oh = b.tick_host(pkg.PROTO_INTELLIGENT, pkg.POLICY_GIVEN, pkg.OBS_CLIP, actions_host=ah, join=(t % 2 == 0))
+        b.host_join()
+        torch.cuda.synchronize()
+        assert np.array_equal(o["act"].cpu().numpy(), oh["act"].numpy()), t
+        assert np.array_equal(o["reward"].cpu().numpy(), oh["reward"].numpy()), t
+        assert np.array_equal(o["done"].cpu().numpy(), oh["done"].numpy()), t
+        took = o["act"].cpu().numpy() >= 0
+        assert np.array_equal(o["obs"].float().cpu().numpy()[took], oh["obs"].float().cpu().numpy()[took]), t
+        hist.append(int(took.sum()))
+    assert sum(hist) > 0
+    ha, aa = a.get_state(); hb, ab = b.get_state()
+    assert np.array_equal(ha, hb) and np.array_equal(aa, ab)
+    a.close(); b.close()
