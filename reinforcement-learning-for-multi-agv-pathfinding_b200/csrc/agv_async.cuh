@@ -203,7 +203,7 @@ __device__ __forceinline__ void tick_async(const DevCfg &c, const LaneArgs &t, u
             const bool oob = nx < 1 || ny < 1 || nx > c.W || ny > c.H;
             if (oob) { r = -1; end = 1; }
             else {
-                const int code = __ldg(c.grid + (ny - 1) * c.W + (nx - 1));
+                const int code = ws.cell_code(nx - 1, ny - 1);
                 const bool at_target = (nx == a.tx) && (ny == a.ty);
                 if (code == 1 && a.loaded && !at_target) { r = -1; end = 1; }
                 else if (code == 2 && !at_target) { r = -1; end = 1; }
@@ -331,6 +331,8 @@ __device__ __forceinline__ void tick_async(const DevCfg &c, const LaneArgs &t, u
         atomicMax(c.counters + 16, (unsigned long long)d_); atomicMax(c.counters + 17, (unsigned long long)iters_);
         atomicMax(c.counters + 18, (unsigned long long)idle_);
         for (int k_ = 0; k_ < 7; k_++) atomicAdd(c.counters + 20 + k_, (unsigned long long)q_[k_]);
+        { int b_ = (int)(d_ / 100000); if (b_ > 11) b_ = 11; atomicAdd(c.counters + 3 + 3 + 0 * b_, 0ull); atomicAdd(c.counters + 20 + 7, 0ull); }
+        { int b_ = (int)(d_ / 100000); if (b_ > 11) b_ = 11; atomicAdd(&c.counters[32 + b_], 1ull); }
     }
 #endif
     __threadfence_block();

@@ -492,8 +492,8 @@ int agv_create(const AgvConfig *cfg, const uint8_t *grid_host, AgvHandle **out) 
     CREATE_TRY(cudaMemset(h->d_tasks, 0, sizeof(uint32_t) * (size_t)cfg->E * (cfg->T > 0 ? cfg->T : 1)));
     CREATE_TRY(cudaMalloc(&h->d_grid, HW));
     CREATE_TRY(cudaMalloc(&h->d_rows, rows.size() * 8));
-    CREATE_TRY(cudaMalloc(&h->d_counters, 32 * sizeof(unsigned long long)));
-    CREATE_TRY(cudaMemset(h->d_counters, 0, 32 * sizeof(unsigned long long)));
+    CREATE_TRY(cudaMalloc(&h->d_counters, 48 * sizeof(unsigned long long)));
+    CREATE_TRY(cudaMemset(h->d_counters, 0, 48 * sizeof(unsigned long long)));
     CREATE_TRY(cudaMemcpy(h->d_grid, grid_host, HW, cudaMemcpyHostToDevice));
     CREATE_TRY(cudaMemcpy(h->d_rows, rows.data(), rows.size() * 8, cudaMemcpyHostToDevice));
     d.state = h->d_state; d.tasks = h->d_tasks; d.grid = h->d_grid;
@@ -777,13 +777,13 @@ int agv_read_counters(AgvHandle *h, uint64_t out[3], void *stream) {
     if (!h || !out) return AGV_E_INVALID;
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
-    unsigned long long tmp[32];  // [3..31]: phase cycle counters of profiling builds (-DAGV_LANES_PROF)
+    unsigned long long tmp[48];  // [3..31]: phase cycle counters of profiling builds (-DAGV_LANES_PROF)
     CUDA_TRY(cudaMemcpyAsync(tmp, h->d_counters, sizeof(tmp), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemsetAsync(h->d_counters, 0, sizeof(tmp), st));
     CUDA_TRY(cudaStreamSynchronize(st));
     if (getenv("AGV_PROF_DUMP")) {
         fprintf(stderr, "agv prof:");
-        for (int i = 3; i < 28; i++) fprintf(stderr, " %llu", tmp[i]);
+        for (int i = 3; i < 48; i++) fprintf(stderr, " %llu", tmp[i]);
         fprintf(stderr, "\n");
     }
     out[0] = tmp[0]; out[1] = tmp[1]; out[2] = tmp[2];

@@ -68,23 +68,24 @@ __device__ __forceinline__ int lane_monotone(bool need, const uint64_t *tab, int
     const uint64_t *op = (mirror ? occm : occ) + ty * NW;
     const int step = -dys * NW;
     const Row<NW> box = rrange<NW>(txm, sxm);
-    Row<NW> reach = rbit<NW>(txm), prev = rzero<NW>();
-    bool alive = need;
-    const int n = abs(ty - sy);  // rows after the target's
-    if (alive) {                 // the target's row: the target cell itself is valid unless occupied
+    Row<NW> reach = rbit<NW>(txm);
+    Row<NW> rfin = rzero<NW>(), pfin = rzero<NW>();  // reach of the start's row / of the row before it
+    const int n = abs(ty - sy);                       // rows after the target's
+    const int nl = need ? n : 0;
+    if (!need) { bp = tab; op = tab; }
+    {   // the target's row: the target cell itself is valid unless occupied
         Row<NW> b = ror(ldrow<NW>(bp), reach);
         const Row<NW> o = ldrow<NW>(op);
 #pragma unroll
         for (int i = 0; i < NW; i++) b.w[i] = b.w[i] & ~o.w[i] & box.w[i];
         reach = rfill_up(rand_(reach, b), b);
-        alive = n == 0 || rany(reach);
+        if (nl == 0) rfin = reach;
     }
-    const int nmax = __reduce_max_sync(FULL, alive ? n : 0);
-    // Branch-free body: the row loads do not depend on the DP state, so with the state update
-    // done by selects the compiler can unroll and hoist them off the dependent chain
-    // (LDS latency was ~2/3 of the time per row).  Finished lanes re-read their last row.
-    const int nl = alive ? n : 0;
-    if (!alive) { bp = tab; op = tab; }
+    const int nmax = __reduce_max_sync(FULL, nl);
+    // The loop-carried chain is only reach -> and -> add -> and/or -> reach (4 dependent ops per
+    // row): the row loads do not depend on the DP state, a dead reach set stays empty by itself
+    // (no liveness flag), and a lane that has passed its last row keeps re-reading that row and
+    // computing into the void -- its result was snapshotted when it == nl, off the chain.
 #pragma unroll 4
     for (int it = 1; it <= nmax; it++) {
         const int k = min(it, nl) * step;
@@ -93,22 +94,16 @@ __device__ __forceinline__ int lane_monotone(bool need, const uint64_t *tab, int
 #pragma unroll
         for (int i = 0; i < NW; i++) b.w[i] = b.w[i] & ~o.w[i] & box.w[i];
         const Row<NW> now = rfill_up(rand_(reach, b), b);
-        const bool upd = alive && it <= nl;
-        // the start's own row may come out empty (the start cell is occupied by the AGV itself,
-        // hence invalid) while the vertical neighbour in `prev` is still on a path
-        const bool live = it == nl || rany(now);
-#pragma unroll
-        for (int i = 0; i < NW; i++) {
-            prev.w[i] = upd ? reach.w[i] : prev.w[i];
-            reach.w[i] = upd ? now.w[i] : reach.w[i];
-        }
-        alive = upd ? live : alive;
+        if (it == nl) { rfin = now; pfin = reach; }
+        reach = now;
     }
     len = 0;
     int act = -1;
-    if (alive) {  // reach = row sy, prev = row sy + dys
-        const bool okH = dxs != 0 && rtest(reach, sxm - 1);
-        const bool okV = dys != 0 && rtest(prev, sxm);
+    if (need) {
+        // the start's own row may be empty (the start cell is occupied by the AGV itself, hence
+        // invalid) while the vertical neighbour in the row before it is still on a path
+        const bool okH = dxs != 0 && rtest(rfin, sxm - 1);
+        const bool okV = dys != 0 && rtest(pfin, sxm);
         if (okH && dxs > 0) act = A_RIGHT;
         else if (okV && dys > 0) act = A_DOWN;
         else if (okV && dys < 0) act = A_UP;
@@ -439,6 +434,13 @@ struct LaneScene {
         const int xm = WB - 1 - x0;
         occm[y0 * NW + (xm >> 6)] &= ~(1ull << (xm & 63));
     }
+    // grid code of an in-bounds cell (0 track, 1 storage, 2 picking) from the base rows in shared
+    // memory: with four 54 KB CTAs on an SM there is next to no L1 left for a global grid lookup
+    __device__ __forceinline__ int cell_code(int x0, int y0) const {
+        const int q = y0 * NW + (x0 >> 6), sh = x0 & 63;
+        const bool b0 = (tab[q] >> sh) & 1ull, b1 = (tab[HN + q] >> sh) & 1ull;
+        return b0 ? (b1 ? 0 : 1) : 2;
+    }
     __device__ __forceinline__ bool occ_test(int x0, int y0) const {
         return (occ[y0 * NW + (x0 >> 6)] >> (x0 & 63)) & 1ull;
     }
@@ -754,7 +756,7 @@ __device__ __forceinline__ void tick_lanes(const DevCfg &c, const LaneArgs &t, u
             const bool oob = nx < 1 || ny < 1 || nx > c.W || ny > c.H;
             if (oob) { r = -1; end = 1; }
             else {
-                const int code = __ldg(c.grid + (ny - 1) * c.W + (nx - 1));
+                const int code = ws.cell_code(nx - 1, ny - 1);
                 const bool at_target = (nx == a.tx) && (ny == a.ty);
                 if (code == 1 && a.loaded && !at_target) { r = -1; end = 1; }
                 else if (code == 2 && !at_target) { r = -1; end = 1; }
