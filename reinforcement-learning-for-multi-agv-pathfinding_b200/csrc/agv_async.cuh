@@ -7,9 +7,11 @@
 // exists inside a scene (Scene.py:124-162), so lanes never have to wait for each other: the
 // tick ends when the slowest SCENE is done, not after 64 x (slowest lane of each iteration).
 //
-// Warp roles in a CTA:  warp 0           scene warp (SPW scenes, one per lane)
-//                       warps 1..NB      BFS workers  (claim posted requests, warp_bfs)
-//                       warp NB+1        record writer (OBS_CLIP: expands 49-bit windows
+// Warp roles in a CTA:  warp 0           scene warp of the light scenes (one scene per lane)
+//                       warp 1           scene warp of the heavy scenes (same lane <-> scene map;
+//                                        a scene is heavy when its last tick needed many BFS)
+//                       warps 2..NB+1    BFS workers  (claim posted requests, warp_bfs)
+//                       warp NB+2        record writer (OBS_CLIP: expands 49-bit windows
 //                                        to [3,7,7] bf16 records and stores them)
 // All hand-offs are flags in shared memory (fence + volatile), polled with __nanosleep.
 // Covers OBS_NONE and OBS_CLIP with K = 7 without the shaped reward; the other variants
@@ -24,12 +26,22 @@ struct AsyncShared {
     unsigned bfs_req[32];    // coop_bfs request word
     unsigned bfs_res[32];    // action | len << 8
     int exit_flag;
-    unsigned enc_seq;        // record batches posted by the scene warp
-    unsigned enc_done;       // record batches written by the record writer
-    int enc_n[2];
-    int pad[3];
-    uint4 enc_req[2][64];    // {window lo, window hi, tpos | which << 8, record index}
+    unsigned done_warps;     // scene warps that have finished their lanes
+    int pad[2];
+    // record batches, one queue per scene warp (q = 0 light scenes, 1 heavy scenes)
+    unsigned enc_seq[2];     // batches posted
+    unsigned enc_done[2];    // batches written by the record writer
+    int enc_n[2][2];
+    uint4 enc_req[2][2][64]; // {window lo, window hi, tpos | which << 8, record index}
 };
+
+// A scene whose previous tick needed at least this many BFS searches is "heavy": it is carried by
+// the CTA's second scene warp, whose iterations are short (few lanes), instead of dragging along
+// (and being slowed down by) the 30-odd light scenes of the first.  The count lives in the scene
+// header's reserved word.
+#ifndef AGV_HEAVY_BFS
+#define AGV_HEAVY_BFS 16
+#endif
 
 constexpr int LS_START = 0, LS_WAIT = 1, LS_HAVE = 2, LS_DONE = 3;
 #ifndef AGV_POLL_NS
@@ -83,46 +95,52 @@ __device__ __forceinline__ void async_bfs_worker(const DevCfg &c, const LaneArgs
 __device__ __forceinline__ void async_record_writer(const LaneArgs &t, uint8_t *smem) {
     const int lane = threadIdx.x & 31;
     AsyncShared *sh = reinterpret_cast<AsyncShared *>(smem + t.off_queue);
-    volatile unsigned *vseq = &sh->enc_seq, *vdone = &sh->enc_done;
+    volatile unsigned *vseq = sh->enc_seq, *vdone = sh->enc_done;
     volatile int *vexit = &sh->exit_flag;
-    unsigned mine = 0;
+    unsigned mine[2] = {0, 0};
     for (;;) {
-        if (*vseq == mine) {
-            if (*vexit) {
-                if (*vseq == mine) return;  // the last batch is posted before the exit flag
-                continue;
+        bool any = false;
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            if (vseq[q] == mine[q]) continue;
+            any = true;
+            __threadfence_block();
+            const int buf = mine[q] & 1;
+            const int n = *reinterpret_cast<volatile int *>(&sh->enc_n[q][buf]);
+            for (int r = 0; r < n; r++) {
+                const uint4 rq = sh->enc_req[q][buf][r];
+                uint16_t *base = (rq.z >> 8) ? t.next_obs : t.obs;
+                expand_clip7(base + (size_t)rq.w * 147, (uint64_t)rq.x | ((uint64_t)rq.y << 32), (int)(rq.z & 255u), lane);
             }
-            __nanosleep(AGV_POLL_NS);
+            __threadfence_block();
+            __syncwarp();
+            mine[q]++;
+            if (lane == 0) vdone[q] = mine[q];
+        }
+        if (any) continue;
+        if (*vexit) {  // the last batches are posted before the exit flag
+            if (vseq[0] == mine[0] && vseq[1] == mine[1]) return;
             continue;
         }
-        __threadfence_block();
-        const int buf = mine & 1;
-        const int n = *reinterpret_cast<volatile int *>(&sh->enc_n[buf]);
-        for (int r = 0; r < n; r++) {
-            const uint4 rq = sh->enc_req[buf][r];
-            uint16_t *base = (rq.z >> 8) ? t.next_obs : t.obs;
-            expand_clip7(base + (size_t)rq.w * 147, (uint64_t)rq.x | ((uint64_t)rq.y << 32), (int)(rq.z & 255u), lane);
-        }
-        __threadfence_block();
-        __syncwarp();
-        mine++;
-        if (lane == 0) *vdone = mine;
+        __nanosleep(AGV_POLL_NS);
     }
 }
 
 // scene warp
+// scene warp `which` (0: the light scenes of the CTA, 1: its heavy scenes)
 template <int NW, int RPL, int OBS, int SPW>
-__device__ __forceinline__ void tick_async(const DevCfg &c, const LaneArgs &t, uint8_t *smem) {
+__device__ __forceinline__ void tick_async(const DevCfg &c, const LaneArgs &t, uint8_t *smem, const int which) {
     const int lane = threadIdx.x & 31;
     const int e0 = blockIdx.x * SPW;
     LaneScene<NW, RPL, SPW, 0> ws(c, t, smem, lane, e0);
     AsyncShared *sh = reinterpret_cast<AsyncShared *>(smem + t.off_queue);
     volatile unsigned *vs = sh->bfs_state;
-    volatile unsigned *vseq = &sh->enc_seq, *vdone = &sh->enc_done;
-    ws.load_tables();
-    ws.load_blocks(e0);
+    volatile unsigned *vseq = &sh->enc_seq[which], *vdone = &sh->enc_done[which];
     const int N = c.N;
-    {   // per-AGV outputs default to "no turn"
+    if (which == 0) {
+        ws.load_tables();
+        ws.load_blocks(e0);
+        // per-AGV outputs default to "no turn"
         const int nsc = min(SPW, c.E - e0);
         const size_t r0 = (size_t)e0 * N;
         for (int q = lane; q < nsc * N; q += 32) {
@@ -132,8 +150,11 @@ __device__ __forceinline__ void tick_async(const DevCfg &c, const LaneArgs &t, u
             if (t.plen) t.plen[r0 + q] = 0;
             if (t.slen) t.slen[r0 + q] = 0xFFFF;
         }
-        __syncwarp();
+        __threadfence_block();
     }
+    named_bar_sync(3, 64);  // both scene warps: tables, scene blocks and default outputs are in place
+    if (ws.has) ws.has = ((ws.hdr_w[6] >= (unsigned)AGV_HEAVY_BFS) ? 1 : 0) == which;
+    unsigned n_bfs = 0;
     bool live = ws.has;
     if (ws.has) {
         ws.hdr_to_regs();
@@ -167,6 +188,15 @@ __device__ __forceinline__ void tick_async(const DevCfg &c, const LaneArgs &t, u
 #endif
     while (__any_sync(FULL, st != LS_DONE)) {
         bool progress = false;
+        // nothing to do while every unfinished scene of this warp waits for its BFS: sleep instead of
+        // running the (predicated-off) body, whose instructions would compete with the BFS workers
+        if (!__any_sync(FULL, st == LS_START || st == LS_HAVE || (st == LS_WAIT && vs[lane] == 3u))) {
+#ifdef AGV_LANES_PROF
+            iters_++; idle_++;
+#endif
+            __nanosleep(100);
+            continue;
+        }
         // ---- A: answers of the BFS workers
         if (st == LS_WAIT && vs[lane] == 3u) {
             __threadfence_block();
@@ -243,7 +273,7 @@ __device__ __forceinline__ void tick_async(const DevCfg &c, const LaneArgs &t, u
                 const uint64_t wm = lane_window7<NW>(ws.tab + a.loaded * ws.HN, ws.occ, c.H, a.x - 1, a.y - 1, a.tx - 1,
                                                      a.ty - 1, shared);
                 const int tpos = (max(-3, min(3, a.ty - a.y)) + 3) * 7 + max(-3, min(3, a.tx - a.x)) + 3;
-                sh->enc_req[buf][nrec + __popc(pend & ((1u << lane) - 1u))] =
+                sh->enc_req[which][buf][nrec + __popc(pend & ((1u << lane) - 1u))] =
                     make_uint4((unsigned)wm, (unsigned)(wm >> 32), (unsigned)tpos | 256u, (unsigned)(ws.e * N + i));
             }
             nrec += __popc(pend);
@@ -274,13 +304,13 @@ __device__ __forceinline__ void tick_async(const DevCfg &c, const LaneArgs &t, u
                 const uint64_t wm = lane_window7<NW>(ws.tab + a.loaded * ws.HN, ws.occ, c.H, a.x - 1, a.y - 1, a.tx - 1,
                                                      a.ty - 1, shared);
                 const int tpos = (max(-3, min(3, a.ty - a.y)) + 3) * 7 + max(-3, min(3, a.tx - a.x)) + 3;
-                sh->enc_req[buf][nrec + __popc(pend & ((1u << lane) - 1u))] =
+                sh->enc_req[which][buf][nrec + __popc(pend & ((1u << lane) - 1u))] =
                     make_uint4((unsigned)wm, (unsigned)(wm >> 32), (unsigned)tpos, (unsigned)(ws.e * N + i));
             }
             nrec += __popc(pend);
         }
         QP(4)
-        {
+        if (__any_sync(FULL, act)) {
             const bool guided = (t.policy == POLICY_GUIDED) || (t.policy == POLICY_GIVEN && given < 0);
             const bool pol_a = !guided && t.policy == POLICY_ASTAR;
             bool need = act && (guided || pol_a);
@@ -304,13 +334,14 @@ __device__ __forceinline__ void tick_async(const DevCfg &c, const LaneArgs &t, u
                     __threadfence_block();
                     vs[lane] = 1u;
                     st = LS_WAIT;
+                    n_bfs++;
                 }
             }
         }
         QP(5)
         // ---- hand the iteration's records to the record writer
         if (nrec > 0) {
-            if (lane == 0) *reinterpret_cast<volatile int *>(&sh->enc_n[buf]) = nrec;
+            if (lane == 0) *reinterpret_cast<volatile int *>(&sh->enc_n[which][buf]) = nrec;
             __threadfence_block();
             __syncwarp();
             seq++;
@@ -321,10 +352,14 @@ __device__ __forceinline__ void tick_async(const DevCfg &c, const LaneArgs &t, u
         iters_++;
         if (!__any_sync(FULL, progress)) idle_++;
 #endif
-        if (!__any_sync(FULL, progress)) __nanosleep(60);  // only scenes waiting for a BFS are left
     }
 #ifdef AGV_LANES_PROF
-    if (lane == 0) {
+#ifndef AGV_PROF_WHICH
+#define AGV_PROF_WHICH 1
+#endif
+    const unsigned mb_ = __reduce_max_sync(FULL, n_bfs);
+    if (lane == 0 && which == AGV_PROF_WHICH) {
+        atomicMax(c.counters + 19, (unsigned long long)mb_);
         const long long d_ = clock64() - p0_;
         atomicAdd(c.counters + 3 + 0, (unsigned long long)d_); atomicAdd(c.counters + 3 + 1, (unsigned long long)iters_);
         atomicAdd(c.counters + 3 + 2, (unsigned long long)idle_); atomicAdd(c.counters + 15, 1ull);
@@ -337,9 +372,9 @@ __device__ __forceinline__ void tick_async(const DevCfg &c, const LaneArgs &t, u
 #endif
     __threadfence_block();
     __syncwarp();
-    if (lane == 0) *reinterpret_cast<volatile int *>(&sh->exit_flag) = 1;
+    if (lane == 0 && atomicAdd(&sh->done_warps, 1u) == 1u) *reinterpret_cast<volatile int *>(&sh->exit_flag) = 1;
     if (live && !ws.over) ws.spawn();
-    if (ws.has) ws.regs_to_hdr();
+    if (ws.has) { ws.regs_to_hdr(); ws.hdr_w[6] = n_bfs; }
     {
         const unsigned ct = __reduce_add_sync(FULL, ws.cnt_turns), ce = __reduce_add_sync(FULL, ws.cnt_ended),
                        cb = __reduce_add_sync(FULL, ws.cnt_bad);
@@ -349,7 +384,9 @@ __device__ __forceinline__ void tick_async(const DevCfg &c, const LaneArgs &t, u
             if (cb) atomicAdd(c.counters + 2, (unsigned long long)cb);
         }
     }
-    ws.store_blocks(e0);
+    __threadfence_block();
+    named_bar_sync(3, 64);  // the headers of both scene warps are back in the blocks
+    if (which == 0) ws.store_blocks(e0);
 }
 
 // kernel body: role by warp index
@@ -359,11 +396,14 @@ __device__ __forceinline__ void async_cta(const DevCfg &c, const LaneArgs &t, ui
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0) {
         sh->bfs_state[lane] = 0u;
-        if (lane == 0) { sh->exit_flag = 0; sh->enc_seq = 0u; sh->enc_done = 0u; }
+        if (lane == 0) {
+            sh->exit_flag = 0; sh->done_warps = 0u;
+            sh->enc_seq[0] = sh->enc_seq[1] = 0u; sh->enc_done[0] = sh->enc_done[1] = 0u;
+        }
     }
     __syncthreads();
-    if (warp == 0) tick_async<NW, RPL, OBS, SPW>(c, t, smem);
-    else if (warp <= NB) async_bfs_worker<NW, RPL, SPW>(c, t, smem);
+    if (warp < 2) tick_async<NW, RPL, OBS, SPW>(c, t, smem, warp);
+    else if (warp < 2 + NB) async_bfs_worker<NW, RPL, SPW>(c, t, smem);
     else async_record_writer(t, smem);
 }
 

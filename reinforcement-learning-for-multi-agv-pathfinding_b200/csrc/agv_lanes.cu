@@ -20,9 +20,9 @@ __global__ void __launch_bounds__(32 * (1 + NWK)) k_tick_lanes(const DevCfg c, c
     else tick_lanes<NW, RPL, OBS, SHAPED, SPW, NWK>(c, t, lane_smem);
 }
 
-// decoupled lanes: scene warp + NB BFS workers (+ the record writer for OBS_CLIP)
+// decoupled lanes: two scene warps (light / heavy scenes) + NB BFS workers (+ the record writer for OBS_CLIP)
 template <int NW, int RPL, int OBS, int SPW, int NB>
-__global__ void __launch_bounds__(32 * (1 + NB + (OBS == OBS_CLIP ? 1 : 0))) k_tick_async(const DevCfg c, const LaneArgs t) {
+__global__ void __launch_bounds__(32 * (2 + NB + (OBS == OBS_CLIP ? 1 : 0))) k_tick_async(const DevCfg c, const LaneArgs t) {
     extern __shared__ __align__(16) uint8_t lane_smem[];
     async_cta<NW, RPL, OBS, SPW, NB>(c, t, lane_smem);
 }
@@ -56,7 +56,7 @@ static int launch_async(const DevCfg &dc, LaneArgs t, cudaStream_t st) {
     }
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     const int ctas = (dc.E + SPW - 1) / SPW;
-    kern<<<ctas, 32 * (1 + NB + (OBS == OBS_CLIP ? 1 : 0)), smem, st>>>(dc, t);
+    kern<<<ctas, 32 * (2 + NB + (OBS == OBS_CLIP ? 1 : 0)), smem, st>>>(dc, t);
     note_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { note_cuda_error((int)e); return -2; }
