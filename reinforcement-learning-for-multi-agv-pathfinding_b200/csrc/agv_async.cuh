@@ -177,6 +177,8 @@ __device__ __forceinline__ void tick_async(const DevCfg &c, const LaneArgs &t, u
     long long iters_ = 0, idle_ = 0;
 #endif
     int i = 0, st = n_loop > 0 ? LS_START : LS_DONE;
+    Agv a;  // the AGV of the turn in progress (kept in registers from phase C to phase B)
+    a.x = a.y = a.tx = a.ty = 1; a.stage = a.loaded = a.idle = a.order = 0;
     int action = -1, plen = 0, given = -1;
     bool guard = false;
     unsigned seq = 0;
@@ -218,11 +220,8 @@ __device__ __forceinline__ void tick_async(const DevCfg &c, const LaneArgs &t, u
         // ---- B: finish the turn of the lanes that have their action
         // (Explorer.check_action, Explorer.py:151-208; Scene.py:155-158)
         const bool fin = st == LS_HAVE;
-        Agv a;
-        a.x = a.y = a.tx = a.ty = 1; a.stage = a.loaded = a.idle = a.order = 0;
-        if (fin) {
+        if (fin) {  // `a` is still the AGV loaded when this turn started
             progress = true;
-            a = ws.load_agv(i);
             const bool guided = (t.policy == POLICY_GUIDED) || (t.policy == POLICY_GIVEN && given < 0);
             const bool pol_a = !guided && t.policy == POLICY_ASTAR;
             if (!guided && !pol_a && action > A_STOP) { ws.cnt_bad++; action = A_STOP; }
@@ -237,16 +236,15 @@ __device__ __forceinline__ void tick_async(const DevCfg &c, const LaneArgs &t, u
                 const bool at_target = (nx == a.tx) && (ny == a.ty);
                 if (code == 1 && a.loaded && !at_target) { r = -1; end = 1; }
                 else if (code == 2 && !at_target) { r = -1; end = 1; }
-                else if (t.proto == PROTO_INTELLIGENT && ws.other_at(i, nx | (ny << 8))) { r = -1; end = 1; }
+                else if (t.proto == PROTO_INTELLIGENT && ws.other_at_from(i, nx | (ny << 8), a.x | (a.y << 8))) { r = -1; end = 1; }
                 else if (at_target) { r = 1; ws.continue_working(a); }
             }
             // Explorer.py:145-148: the move is applied iff not is_end
             if (t.proto != PROTO_INTELLIGENT && !guided && !pol_a) ws.overlap = true;
             if (!end && (dx | dy)) {
-                const bool still = ws.other_at(i, a.x | (a.y << 8));
-                if (!still) ws.occ_clear(a.x - 1, a.y - 1);
+                const bool still = ws.other_at_from(i, a.x | (a.y << 8), a.x | (a.y << 8));
+                ws.occ_move(a.x - 1, a.y - 1, nx - 1, ny - 1, !still);
                 a.x = nx; a.y = ny;
-                ws.occ_set(nx - 1, ny - 1);
             }
             ws.store_agv(i, a);
             if (t.proto == PROTO_INTELLIGENT) {

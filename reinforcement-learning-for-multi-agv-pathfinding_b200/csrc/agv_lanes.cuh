@@ -118,31 +118,36 @@ __device__ __forceinline__ int lane_monotone(bool need, const uint64_t *tab, int
 template <int NW>
 __device__ __forceinline__ uint64_t lane_window7(const uint64_t *tabl, const uint64_t *occ, int H, int cx, int cy,
                                                  int tx0, int ty0, bool shared) {
+    // Branch-free: rows outside the map are clamped for the load and masked afterwards, the own /
+    // target bits go in by selects -- so all 14 row loads issue up front instead of one
+    // load-latency per row behind a branch (the window was 1 k of the ~5 k cycles of a turn).
     uint64_t wm = 0ull;
     const int lo = cx - 3;
+    const Row<NW> ownb = rbit<NW>(cx), tgtb = rbit<NW>(tx0);
 #pragma unroll
     for (int wy = 0; wy < 7; wy++) {
-        const int r = cy - 3 + wy;
-        if (r >= 0 && r < H) {
-            Row<NW> b = ldrow<NW>(tabl + r * NW), o = ldrow<NW>(occ + r * NW);
-            if (r == ty0) b = ror(b, rbit<NW>(tx0));
-            if (r == cy) { b = ror(b, rbit<NW>(cx)); if (!shared) o = randn(o, rbit<NW>(cx)); }
-            b = randn(b, o);
-            uint64_t bits;
-            if (NW == 1) {
-                bits = lo >= 0 ? (b.w[0] >> lo) : (b.w[0] << (-lo));
-            } else {
-                if (lo < 0) bits = b.w[0] << (-lo);
-                else {
-                    const int wi = lo >> 6, off = lo & 63;
-                    uint64_t a0 = 0ull, a1 = 0ull;
+        const int r = cy - 3 + wy, rc = min(max(r, 0), H - 1);
+        Row<NW> b = ldrow<NW>(tabl + rc * NW), o = ldrow<NW>(occ + rc * NW);
+        const bool is_t = r == ty0, is_o = r == cy;
 #pragma unroll
-                    for (int i = 0; i < NW; i++) { if (i == wi) a0 = b.w[i]; if (i == wi + 1) a1 = b.w[i]; }
-                    bits = (a0 >> off) | (off ? (a1 << (64 - off)) : 0ull);
-                }
-            }
-            wm |= (bits & 0x7Full) << (7 * wy);
+        for (int i = 0; i < NW; i++) {
+            const uint64_t ob = is_o ? ownb.w[i] : 0ull;
+            b.w[i] = (b.w[i] | (is_t ? tgtb.w[i] : 0ull) | ob) & ~(o.w[i] & ~(shared ? 0ull : ob));
         }
+        uint64_t bits;
+        if (NW == 1) {
+            bits = lo >= 0 ? (b.w[0] >> lo) : (b.w[0] << (-lo));
+        } else {
+            if (lo < 0) bits = b.w[0] << (-lo);
+            else {
+                const int wi = lo >> 6, off = lo & 63;
+                uint64_t a0 = 0ull, a1 = 0ull;
+#pragma unroll
+                for (int i = 0; i < NW; i++) { if (i == wi) a0 = b.w[i]; if (i == wi + 1) a1 = b.w[i]; }
+                bits = (a0 >> off) | (off ? (a1 << (64 - off)) : 0ull);
+            }
+        }
+        wm |= (r == rc) ? ((bits & 0x7Full) << (7 * wy)) : 0ull;
     }
     return wm;
 }
@@ -440,6 +445,27 @@ struct LaneScene {
         const int q = y0 * NW + (x0 >> 6), sh = x0 & 63;
         const bool b0 = (tab[q] >> sh) & 1ull, b1 = (tab[HN + q] >> sh) & 1ull;
         return b0 ? (b1 ? 0 : 1) : 2;
+    }
+    // AGV moves (x0,y0) -> (x1,y1): the four row loads (plain + mirrored copy) issue together
+    __device__ __forceinline__ void occ_move(int x0, int y0, int x1, int y1, bool clear_old) {
+        const int q0 = y0 * NW + (x0 >> 6), q1 = y1 * NW + (x1 >> 6);
+        const int xm0 = WB - 1 - x0, xm1 = WB - 1 - x1;
+        const int p0 = y0 * NW + (xm0 >> 6), p1 = y1 * NW + (xm1 >> 6);
+        const uint64_t b0 = clear_old ? (1ull << (x0 & 63)) : 0ull, b1 = 1ull << (x1 & 63);
+        const uint64_t c0 = clear_old ? (1ull << (xm0 & 63)) : 0ull, c1 = 1ull << (xm1 & 63);
+        uint64_t r0 = occ[q0], r1 = occ[q1], m0 = occm[p0], m1 = occm[p1];
+        if (q0 == q1) { r1 = (r1 & ~b0) | b1; occ[q1] = r1; }
+        else { occ[q0] = r0 & ~b0; occ[q1] = r1 | b1; }
+        if (p0 == p1) { m1 = (m1 & ~c0) | c1; occm[p1] = m1; }
+        else { occm[p0] = m0 & ~c0; occm[p1] = m1 | c1; }
+    }
+    // other_at for the AGV whose (unmoved) position `mypos` is already in registers
+    __device__ __forceinline__ bool other_at_from(int i, int cell, int mypos) const {
+        if (!overlap) {
+            if (mypos == cell) return false;
+            return occ_test((cell & 255) - 1, (cell >> 8) - 1);
+        }
+        return other_at(i, cell);
     }
     __device__ __forceinline__ bool occ_test(int x0, int y0) const {
         return (occ[y0 * NW + (x0 >> 6)] >> (x0 & 63)) & 1ull;
