@@ -33,12 +33,12 @@ template <int NW, int SPW>
 static int plan_lanes(const DevCfg &dc, LaneArgs &t, int n_vrow, int queue_bytes) {
     const int HN = dc.H * NW;
     int off = 0;
-    t.off_tab = off; off += 4 * HN * 8;
+    t.off_tab = off; off += (mirror_copy<NW>() ? 4 : 2) * HN * 8;
     t.blk_stride = dc.env_stride + 4;  // odd number of words: same-field accesses of the 32 lanes hit 32 banks
     t.off_blk = off; off = align8(off + SPW * t.blk_stride);
     t.occ_stride = HN | 1;
     t.off_occ = off; off += SPW * t.occ_stride * 8;
-    t.off_occm = off; off += SPW * t.occ_stride * 8;
+    t.off_occm = off; off += mirror_copy<NW>() ? SPW * t.occ_stride * 8 : 0;
     t.off_vrow = off; off += n_vrow * HN * 8;
     t.off_zero = off; off += HN * 8;
     t.off_queue = (off + 15) & ~15; off = t.off_queue + queue_bytes;

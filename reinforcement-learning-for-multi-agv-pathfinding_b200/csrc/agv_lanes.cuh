@@ -36,6 +36,12 @@ struct LaneArgs {
     int off_zero;    // u64 [H*NW] of zeros: "occupancy" of a matrix that does not block the explorers
 };
 
+// Column-mirrored copies of the occupancy rows / base tables are kept only for maps up to 64 columns
+// (NW = 1): at 128 x 128 they would double the 2 KB of occupancy per scene and halve the number of
+// resident CTAs, so there the row DP mirrors the rows it loads (BREV, off its dependent chain).
+template <int NW>
+__host__ __device__ constexpr bool mirror_copy() { return NW == 1; }
+
 template <int NW>
 __device__ __forceinline__ Row<NW> ldrow(const uint64_t *p) {
     Row<NW> r;
@@ -64,8 +70,9 @@ __device__ __forceinline__ int lane_monotone(bool need, const uint64_t *tab, int
     const int dxs = (tx > sx) - (tx < sx), dys = (ty > sy) - (ty < sy);
     const bool mirror = tx > sx;
     const int sxm = mirror ? WB - 1 - sx : sx, txm = mirror ? WB - 1 - tx : tx;  // txm <= sxm
-    const uint64_t *bp = tab + ((mirror ? 2 : 0) + loaded) * HN + ty * NW;
-    const uint64_t *op = (mirror ? occm : occ) + ty * NW;
+    const bool flip = mirror && !mirror_copy<NW>();  // mirror the loaded rows on the fly
+    const uint64_t *bp = tab + ((mirror && mirror_copy<NW>() ? 2 : 0) + loaded) * HN + ty * NW;
+    const uint64_t *op = (mirror && mirror_copy<NW>() ? occm : occ) + ty * NW;
     const int step = -dys * NW;
     const Row<NW> box = rrange<NW>(txm, sxm);
     Row<NW> reach = rbit<NW>(txm);
@@ -74,8 +81,9 @@ __device__ __forceinline__ int lane_monotone(bool need, const uint64_t *tab, int
     const int nl = need ? n : 0;
     if (!need) { bp = tab; op = tab; }
     {   // the target's row: the target cell itself is valid unless occupied
-        Row<NW> b = ror(ldrow<NW>(bp), reach);
-        const Row<NW> o = ldrow<NW>(op);
+        Row<NW> b = ldrow<NW>(bp), o = ldrow<NW>(op);
+        if (!mirror_copy<NW>() && flip) { b = rmirror(b); o = rmirror(o); }
+        b = ror(b, reach);
 #pragma unroll
         for (int i = 0; i < NW; i++) b.w[i] = b.w[i] & ~o.w[i] & box.w[i];
         reach = rfill_up(rand_(reach, b), b);
@@ -89,8 +97,8 @@ __device__ __forceinline__ int lane_monotone(bool need, const uint64_t *tab, int
 #pragma unroll 4
     for (int it = 1; it <= nmax; it++) {
         const int k = min(it, nl) * step;
-        Row<NW> b = ldrow<NW>(bp + k);
-        const Row<NW> o = ldrow<NW>(op + k);
+        Row<NW> b = ldrow<NW>(bp + k), o = ldrow<NW>(op + k);
+        if (!mirror_copy<NW>() && flip) { b = rmirror(b); o = rmirror(o); }
 #pragma unroll
         for (int i = 0; i < NW; i++) b.w[i] = b.w[i] & ~o.w[i] & box.w[i];
         const Row<NW> now = rfill_up(rand_(reach, b), b);
@@ -387,8 +395,10 @@ struct LaneScene {
             for (int i = 0; i < NW; i++) {
                 tb[0 * HN + r * NW + i] = b0.w[i];
                 tb[1 * HN + r * NW + i] = b1.w[i];
-                tb[2 * HN + r * NW + i] = m0.w[i];
-                tb[3 * HN + r * NW + i] = m1.w[i];
+                if (mirror_copy<NW>()) {
+                    tb[2 * HN + r * NW + i] = m0.w[i];
+                    tb[3 * HN + r * NW + i] = m1.w[i];
+                }
             }
         }
     }
@@ -431,11 +441,13 @@ struct LaneScene {
     // ---- occupancy (cells are 0-based here)
     __device__ __forceinline__ void occ_set(int x0, int y0) {
         occ[y0 * NW + (x0 >> 6)] |= 1ull << (x0 & 63);
+        if (!mirror_copy<NW>()) return;
         const int xm = WB - 1 - x0;
         occm[y0 * NW + (xm >> 6)] |= 1ull << (xm & 63);
     }
     __device__ __forceinline__ void occ_clear(int x0, int y0) {
         occ[y0 * NW + (x0 >> 6)] &= ~(1ull << (x0 & 63));
+        if (!mirror_copy<NW>()) return;
         const int xm = WB - 1 - x0;
         occm[y0 * NW + (xm >> 6)] &= ~(1ull << (xm & 63));
     }
@@ -453,11 +465,14 @@ struct LaneScene {
         const int p0 = y0 * NW + (xm0 >> 6), p1 = y1 * NW + (xm1 >> 6);
         const uint64_t b0 = clear_old ? (1ull << (x0 & 63)) : 0ull, b1 = 1ull << (x1 & 63);
         const uint64_t c0 = clear_old ? (1ull << (xm0 & 63)) : 0ull, c1 = 1ull << (xm1 & 63);
-        uint64_t r0 = occ[q0], r1 = occ[q1], m0 = occm[p0], m1 = occm[p1];
+        uint64_t r0 = occ[q0], r1 = occ[q1], m0 = 0ull, m1 = 0ull;
+        if (mirror_copy<NW>()) { m0 = occm[p0]; m1 = occm[p1]; }
         if (q0 == q1) { r1 = (r1 & ~b0) | b1; occ[q1] = r1; }
         else { occ[q0] = r0 & ~b0; occ[q1] = r1 | b1; }
-        if (p0 == p1) { m1 = (m1 & ~c0) | c1; occm[p1] = m1; }
-        else { occm[p0] = m0 & ~c0; occm[p1] = m1 | c1; }
+        if (mirror_copy<NW>()) {
+            if (p0 == p1) { m1 = (m1 & ~c0) | c1; occm[p1] = m1; }
+            else { occm[p0] = m0 & ~c0; occm[p1] = m1 | c1; }
+        }
     }
     // other_at for the AGV whose (unmoved) position `mypos` is already in registers
     __device__ __forceinline__ bool other_at_from(int i, int cell, int mypos) const {
@@ -471,7 +486,7 @@ struct LaneScene {
         return (occ[y0 * NW + (x0 >> 6)] >> (x0 & 63)) & 1ull;
     }
     __device__ __forceinline__ void build_occ() {
-        for (int q = 0; q < HN; q++) { occ[q] = 0ull; occm[q] = 0ull; }
+        for (int q = 0; q < HN; q++) { occ[q] = 0ull; if (mirror_copy<NW>()) occm[q] = 0ull; }
         bool dup = false;
         for (int j = 0; j < n_created; j++) {
             const int p = pos_s[j], x0 = (p & 255) - 1, y0 = (p >> 8) - 1;
