@@ -403,12 +403,28 @@ struct LaneScene {
         }
     }
     __device__ __forceinline__ void load_blocks(int e0) {
-        const int nsc = min(SPW, c.E - e0), wps = c.env_stride >> 2;
+        // 8 scene blocks (<= 32 words per lane) in flight at a time: the copy is latency-bound
+        // (one DRAM round trip per batch), so batches of independent loads, not a load-store loop
+        const int nsc = min(SPW, c.E - e0), wps = c.env_stride >> 2;  // wps <= 120 (N <= 64)
         const uint32_t *src = reinterpret_cast<const uint32_t *>(c.state + (size_t)e0 * c.env_stride);
-        for (int j = 0; j < nsc; j++) {
-            uint32_t *dst = reinterpret_cast<uint32_t *>(smem + t.off_blk + (size_t)j * t.blk_stride);
-#pragma unroll 4
-            for (int w = lane; w < wps; w += 32) dst[w] = src[j * wps + w];
+        for (int j0 = 0; j0 < nsc; j0 += 8) {
+            uint32_t v[8][4];
+#pragma unroll
+            for (int jj = 0; jj < 8; jj++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int w = lane + 32 * q;
+                    v[jj][q] = (j0 + jj < nsc && w < wps) ? __ldg(src + (j0 + jj) * wps + w) : 0u;
+                }
+#pragma unroll
+            for (int jj = 0; jj < 8; jj++) {
+                uint32_t *dst = reinterpret_cast<uint32_t *>(smem + t.off_blk + (size_t)(j0 + jj) * t.blk_stride);
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int w = lane + 32 * q;
+                    if (j0 + jj < nsc && w < wps) dst[w] = v[jj][q];
+                }
+            }
         }
         __syncwarp();
     }
@@ -486,14 +502,21 @@ struct LaneScene {
         return (occ[y0 * NW + (x0 >> 6)] >> (x0 & 63)) & 1ull;
     }
     __device__ __forceinline__ void build_occ() {
+        // ORs without a returned value (no load -> test -> store chain per AGV); two created AGVs on
+        // one cell show up as fewer set bits than AGVs
         for (int q = 0; q < HN; q++) { occ[q] = 0ull; if (mirror_copy<NW>()) occm[q] = 0ull; }
-        bool dup = false;
         for (int j = 0; j < n_created; j++) {
             const int p = pos_s[j], x0 = (p & 255) - 1, y0 = (p >> 8) - 1;
-            dup |= occ_test(x0, y0);
-            occ_set(x0, y0);
+            // (32-bit halves: the 64-bit shared-memory OR is a compare-and-swap loop)
+            atomicOr(reinterpret_cast<unsigned *>(occ) + y0 * NW * 2 + (x0 >> 5), 1u << (x0 & 31));
+            if (mirror_copy<NW>()) {
+                const int xm = WB - 1 - x0;
+                atomicOr(reinterpret_cast<unsigned *>(occm) + y0 * NW * 2 + (xm >> 5), 1u << (xm & 31));
+            }
         }
-        overlap = dup;
+        int bits = 0;
+        for (int q = 0; q < HN; q++) bits += __popcll(occ[q]);
+        overlap = bits != n_created;
     }
 
     __device__ __forceinline__ Agv load_agv(int i) const {
