@@ -26,6 +26,11 @@ def _nvcc():
     return n
 
 
+def hash_flags(flags) -> int:
+    import zlib
+    return zlib.crc32(" ".join(flags).encode()) & 0xFFFFFFFF
+
+
 def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
@@ -35,15 +40,17 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+    if not force and not needs_build() and not os.environ.get("AGV_NVCC_EXTRA") and _last_flags() == "":
         return LIB
     # one object per translation unit, compiled in parallel and only when stale, then one link
-    os.makedirs(OBJ_DIR, exist_ok=True)
     hdr_t = max(os.path.getmtime(os.path.join(CSRC, h)) for h in HEADERS)
     extra = os.environ.get("AGV_NVCC_EXTRA", "").split()
+    # objects of different flag sets (tuning / profiling builds) live side by side
+    obj_dir = os.path.join(OBJ_DIR, "default" if not extra else "x%08x" % (hash_flags(extra)))
+    os.makedirs(obj_dir, exist_ok=True)
     jobs = []
     for s in SOURCES:
-        src, obj = os.path.join(CSRC, s), os.path.join(OBJ_DIR, s.replace(".cu", ".o"))
+        src, obj = os.path.join(CSRC, s), os.path.join(obj_dir, s.replace(".cu", ".o"))
         stale = force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_t,
                                                                               os.path.getmtime(os.path.abspath(__file__)))
         if stale:
@@ -56,12 +63,23 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError("nvcc failed compiling %s" % s)
         if verbose:
             sys.stderr.write(err)
-    objs = [os.path.join(OBJ_DIR, s.replace(".cu", ".o")) for s in SOURCES]
+    objs = [os.path.join(obj_dir, s.replace(".cu", ".o")) for s in SOURCES]
     r = subprocess.run([_nvcc(), "-shared", "-o", LIB] + objs, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("nvcc failed linking %s" % LIB)
+    with open(os.path.join(OBJ_DIR, "last_flags"), "w") as f:
+        f.write(" ".join(extra))
     return LIB
+
+
+def _last_flags() -> str:
+    """flag set the in-tree .so was last linked from ("" = the default build)"""
+    try:
+        with open(os.path.join(OBJ_DIR, "last_flags")) as f:
+            return f.read().strip()
+    except OSError:
+        return ""
 
 
 if __name__ == "__main__":
