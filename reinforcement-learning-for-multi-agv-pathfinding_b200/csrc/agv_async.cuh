@@ -81,7 +81,17 @@ __device__ __forceinline__ void async_bfs_worker(const DevCfg &c, const LaneArgs
 #endif
         const int ba = coop_bfs<NW, RPL>(pk, tab, HN, occ0 + (size_t)j * t.occ_stride, c.H, c.W, lane, bl);
 #ifdef AGV_LANES_PROF
-        if (lane == 0) { const long long d_ = clock64() - b0_; atomicAdd(c.counters + 3 + 8, (unsigned long long)d_); atomicAdd(c.counters + 3 + 9, 1ull); atomicAdd(c.counters + 3 + 11, (unsigned long long)bl); if (bl == 0) { atomicAdd(c.counters + 3 + 3, (unsigned long long)d_); atomicAdd(c.counters + 3 + 4, 1ull); if (d_ < 1000) atomicAdd(c.counters + 3 + 5, 1ull); else if (d_ < 4000) atomicAdd(c.counters + 3 + 6, 1ull); else if (d_ < 12000) atomicAdd(c.counters + 3 + 7, 1ull); } }
+        if (lane == 0) {  // [11] BFS cycles, [12] searches, [14] path lengths; [6..10]: searches without a path
+            const long long d_ = clock64() - b0_;
+            atomicAdd(c.counters + 11, (unsigned long long)d_);
+            atomicAdd(c.counters + 12, 1ull);
+            atomicAdd(c.counters + 14, (unsigned long long)bl);
+            if (bl == 0) {
+                atomicAdd(c.counters + 6, (unsigned long long)d_);
+                atomicAdd(c.counters + 7, 1ull);
+                atomicAdd(c.counters + (d_ < 1000 ? 8 : (d_ < 4000 ? 9 : 10)), 1ull);
+            }
+        }
 #endif
         if (lane == 0) {
             *reinterpret_cast<volatile unsigned *>(&sh->bfs_res[j]) = (unsigned)ba | ((unsigned)bl << 8);
@@ -126,7 +136,6 @@ __device__ __forceinline__ void async_record_writer(const LaneArgs &t, uint8_t *
     }
 }
 
-// scene warp
 // scene warp `which` (0: the light scenes of the CTA, 1: its heavy scenes)
 template <int NW, int RPL, int OBS, int SPW>
 __device__ __forceinline__ void tick_async(const DevCfg &c, const LaneArgs &t, uint8_t *smem, const int which) {
@@ -364,8 +373,7 @@ __device__ __forceinline__ void tick_async(const DevCfg &c, const LaneArgs &t, u
         atomicMax(c.counters + 16, (unsigned long long)d_); atomicMax(c.counters + 17, (unsigned long long)iters_);
         atomicMax(c.counters + 18, (unsigned long long)idle_);
         for (int k_ = 0; k_ < 7; k_++) atomicAdd(c.counters + 20 + k_, (unsigned long long)q_[k_]);
-        { int b_ = (int)(d_ / 100000); if (b_ > 11) b_ = 11; atomicAdd(c.counters + 3 + 3 + 0 * b_, 0ull); atomicAdd(c.counters + 20 + 7, 0ull); }
-        { int b_ = (int)(d_ / 100000); if (b_ > 11) b_ = 11; atomicAdd(&c.counters[32 + b_], 1ull); }
+        { int b_ = (int)(d_ / 100000); if (b_ > 11) b_ = 11; atomicAdd(&c.counters[32 + b_], 1ull); }  // histogram of loop cycles, 100 k buckets
     }
 #endif
     __threadfence_block();

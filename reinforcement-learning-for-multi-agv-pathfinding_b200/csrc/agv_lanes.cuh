@@ -727,10 +727,26 @@ __device__ __forceinline__ void lane_worker(const DevCfg &c, const LaneArgs &t, 
     }
 }
 
+// Profiling builds (-DAGV_LANES_PROF): clock64 phase counters of the scene warp, summed over CTAs into
+// counters[3..] (dumped by agv_read_counters when AGV_PROF_DUMP is set): [3+k] cycles of phase k
+// (0 prologue, 1 loop head, 2 obs encode, 3 search, 4 check/move/outputs, 5 next_obs encode,
+// 7 epilogue), [11] cycles inside BFS sections, [12] their count, [13] iterations, [15] CTAs,
+// [16..19] maxima over CTAs of total / search / BFS cycles / BFS sections.
 #ifdef AGV_LANES_PROF
 #define PROF_DECL long long pt_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long pc_ = clock64();
 #define PROF(k) { const long long n_ = clock64(); pt_[k] += n_ - pc_; pc_ = n_; }
-#define PROF_FLUSH pt_[8] = ws.pbfs; pt_[9] = ws.pnb; pt_[10] = n_max; if (lane == 0) { { long long tot_ = 0; for (int k_ = 0; k_ < 8; k_++) tot_ += pt_[k_]; atomicMax(c.counters + 16, (unsigned long long)tot_); atomicMax(c.counters + 17, (unsigned long long)pt_[3]); atomicMax(c.counters + 18, (unsigned long long)ws.pbfs); atomicMax(c.counters + 19, (unsigned long long)ws.pnb);} for (int k_ = 0; k_ < 12; k_++) atomicAdd(c.counters + 3 + k_, (unsigned long long)pt_[k_]); atomicAdd(c.counters + 15, 1ull); }
+#define PROF_FLUSH                                                                                   \
+    pt_[8] = ws.pbfs; pt_[9] = ws.pnb; pt_[10] = n_max;                                              \
+    if (lane == 0) {                                                                                 \
+        long long tot_ = 0;                                                                          \
+        for (int k_ = 0; k_ < 8; k_++) tot_ += pt_[k_];                                              \
+        atomicMax(c.counters + 16, (unsigned long long)tot_);                                        \
+        atomicMax(c.counters + 17, (unsigned long long)pt_[3]);                                      \
+        atomicMax(c.counters + 18, (unsigned long long)ws.pbfs);                                     \
+        atomicMax(c.counters + 19, (unsigned long long)ws.pnb);                                      \
+        for (int k_ = 0; k_ < 12; k_++) atomicAdd(c.counters + 3 + k_, (unsigned long long)pt_[k_]); \
+        atomicAdd(c.counters + 15, 1ull);                                                            \
+    }
 #else
 #define PROF_DECL
 #define PROF(k)
