@@ -189,6 +189,7 @@ __device__ __forceinline__ void tick_async(const DevCfg &c, const LaneArgs &t, u
     Agv a;  // the AGV of the turn in progress (kept in registers from phase C to phase B)
     a.x = a.y = a.tx = a.ty = 1; a.stage = a.loaded = a.idle = a.order = 0;
     int action = -1, plen = 0, given = -1;
+    int pf_idx = -1, pf_val = -1;  // prefetched POLICY_GIVEN action of AGV index pf_idx
     bool guard = false;
     unsigned seq = 0;
 #ifdef AGV_LANES_PROF
@@ -301,7 +302,13 @@ __device__ __forceinline__ void tick_async(const DevCfg &c, const LaneArgs &t, u
             progress = true;
             a = ws.load_agv(i);
             given = -1;
-            if (t.policy == POLICY_GIVEN && t.action) given = (int)t.action[(size_t)ws.e * N + i];
+            if (t.policy == POLICY_GIVEN && t.action) {
+                // the action of the next AGV index was requested a turn ago (a global load here would
+                // put ~500 cycles of latency on every turn of the scene's chain)
+                given = (pf_idx == i) ? pf_val : (int)t.action[(size_t)ws.e * N + i];
+                pf_idx = i + 1;
+                pf_val = (i + 1 < N) ? (int)t.action[(size_t)ws.e * N + i + 1] : -1;
+            }
         }
         if (want_obs) {
             const unsigned pend = __ballot_sync(FULL, act);

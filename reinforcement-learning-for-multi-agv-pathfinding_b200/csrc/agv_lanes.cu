@@ -21,8 +21,14 @@ __global__ void __launch_bounds__(32 * (1 + NWK)) k_tick_lanes(const DevCfg c, c
 }
 
 // decoupled lanes: two scene warps (light / heavy scenes) + NB BFS workers (+ the record writer for OBS_CLIP)
+// 4 CTAs per SM hold the 512 CTAs of 16384 scenes in one wave: the 64-column variants are compiled
+// for that register budget (one register too many means 3 CTAs per SM and a second wave, +20 %)
+template <int NW, int RPL>
+constexpr int async_min_ctas() { return NW * RPL <= 2 ? 4 : (NW * RPL <= 4 ? 2 : 1); }
+
 template <int NW, int RPL, int OBS, int SPW, int NB>
-__global__ void __launch_bounds__(32 * (2 + NB + (OBS == OBS_CLIP ? 1 : 0))) k_tick_async(const DevCfg c, const LaneArgs t) {
+__global__ void __launch_bounds__(32 * (2 + NB + (OBS == OBS_CLIP ? 1 : 0)), async_min_ctas<NW, RPL>())
+k_tick_async(const DevCfg c, const LaneArgs t) {
     extern __shared__ __align__(16) uint8_t lane_smem[];
     async_cta<NW, RPL, OBS, SPW, NB>(c, t, lane_smem);
 }
