@@ -122,7 +122,10 @@ int agv_tick(AgvHandle *h, int32_t proto, int32_t policy, int32_t obs_kind,
  * stream from double-buffered device results, so it overlaps the next call's tick;
  * agv_tick_host_join makes `stream` wait for every outstanding copy-back -- after it,
  * anything ordered on `stream` (an event, a synchronize) covers the host results.
- * Callers that need step k's results before issuing step k+1 join after each call. */
+ * Callers that need step k's results before issuing step k+1 join after each call.
+ * The upload of action_host also runs on an internal stream (overlapping the previous
+ * tick): the buffer must hold its final contents when the call is made and stay
+ * untouched until the tick has run. */
 int agv_tick_host(AgvHandle *h, int32_t proto, int32_t policy, int32_t obs_kind,
                   const int8_t *action_host, int8_t *act_out_host, float *reward_host, uint8_t *done_host,
                   void *obs_dev, void *next_obs_dev, void *stream);

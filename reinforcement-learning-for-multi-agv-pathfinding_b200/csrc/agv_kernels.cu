@@ -346,11 +346,12 @@ struct AgvHandle {
     unsigned long long *d_counters = nullptr;
     // staging for agv_tick_host: results are double-buffered on the device and copied back on an
     // internal stream, so the D2H of call k overlaps the tick of call k+1
-    int8_t *d_action = nullptr, *d_act_out[2] = {nullptr, nullptr};
+    int8_t *d_action[2] = {nullptr, nullptr}, *d_act_out[2] = {nullptr, nullptr};
     float *d_reward[2] = {nullptr, nullptr};
     uint8_t *d_done[2] = {nullptr, nullptr};
-    cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_tick[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr, h2d_stream = nullptr;
+    cudaEvent_t ev_tick[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr}, ev_h2d[2] = {nullptr, nullptr};
+    bool tick_pending[2] = {false, false};
     bool copy_pending[2] = {false, false};
     unsigned host_calls = 0;
     std::vector<uint8_t> h_state;
@@ -512,13 +513,14 @@ int agv_destroy(AgvHandle *h) {
     if (!h) return AGV_OK;
     cudaSetDevice(h->cfg.device);
     cudaFree(h->d_state); cudaFree(h->d_tasks); cudaFree(h->d_grid); cudaFree(h->d_rows); cudaFree(h->d_counters);
-    cudaFree(h->d_action);
     for (int b = 0; b < 2; b++) {
-        cudaFree(h->d_act_out[b]); cudaFree(h->d_reward[b]); cudaFree(h->d_done[b]);
+        cudaFree(h->d_action[b]); cudaFree(h->d_act_out[b]); cudaFree(h->d_reward[b]); cudaFree(h->d_done[b]);
         if (h->ev_tick[b]) cudaEventDestroy(h->ev_tick[b]);
         if (h->ev_copy[b]) cudaEventDestroy(h->ev_copy[b]);
+        if (h->ev_h2d[b]) cudaEventDestroy(h->ev_h2d[b]);
     }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
     delete h;
     return AGV_OK;
 }
@@ -618,16 +620,18 @@ int agv_tick_host(AgvHandle *h, int32_t proto, int32_t policy, int32_t obs_kind,
     if (!h) return AGV_E_INVALID;
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     const size_t n = (size_t)h->cfg.E * h->cfg.N;
-    if (!h->d_action) {
-        CUDA_TRY(cudaMalloc(&h->d_action, n));
+    if (!h->copy_stream) {
         for (int b = 0; b < 2; b++) {
+            CUDA_TRY(cudaMalloc(&h->d_action[b], n));
             CUDA_TRY(cudaMalloc(&h->d_act_out[b], n));
             CUDA_TRY(cudaMalloc(&h->d_reward[b], n * sizeof(float)));
             CUDA_TRY(cudaMalloc(&h->d_done[b], n));
             CUDA_TRY(cudaEventCreateWithFlags(&h->ev_tick[b], cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&h->ev_copy[b], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&h->ev_h2d[b], cudaEventDisableTiming));
         }
         CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
     }
     cudaStream_t st = (cudaStream_t)stream;
     const int b = h->host_calls & 1;
@@ -635,12 +639,18 @@ int agv_tick_host(AgvHandle *h, int32_t proto, int32_t policy, int32_t obs_kind,
     if (h->copy_pending[b]) CUDA_TRY(cudaStreamWaitEvent(st, h->ev_copy[b], 0));
     if (policy == AGV_POLICY_GIVEN) {
         if (!action_host) return AGV_E_INVALID;
-        CUDA_TRY(cudaMemcpyAsync(h->d_action, action_host, n, cudaMemcpyHostToDevice, st));
+        // upload on its own stream so that it overlaps the previous call's tick; only ordered after
+        // the tick that last read buffer b (action_host must hold its final contents at call time)
+        if (h->tick_pending[b]) CUDA_TRY(cudaStreamWaitEvent(h->h2d_stream, h->ev_tick[b], 0));
+        CUDA_TRY(cudaMemcpyAsync(h->d_action[b], action_host, n, cudaMemcpyHostToDevice, h->h2d_stream));
+        CUDA_TRY(cudaEventRecord(h->ev_h2d[b], h->h2d_stream));
+        CUDA_TRY(cudaStreamWaitEvent(st, h->ev_h2d[b], 0));
     }
-    int rc = agv_tick(h, proto, policy, obs_kind, policy == AGV_POLICY_GIVEN ? h->d_action : nullptr, h->d_act_out[b],
+    int rc = agv_tick(h, proto, policy, obs_kind, policy == AGV_POLICY_GIVEN ? h->d_action[b] : nullptr, h->d_act_out[b],
                       h->d_reward[b], h->d_done[b], nullptr, nullptr, obs_dev, next_obs_dev, stream);
     if (rc != AGV_OK) return rc;
     CUDA_TRY(cudaEventRecord(h->ev_tick[b], st));
+    h->tick_pending[b] = true;
     CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_tick[b], 0));
     if (act_out_host) CUDA_TRY(cudaMemcpyAsync(act_out_host, h->d_act_out[b], n, cudaMemcpyDeviceToHost, h->copy_stream));
     if (reward_host) CUDA_TRY(cudaMemcpyAsync(reward_host, h->d_reward[b], n * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
