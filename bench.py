@@ -497,7 +497,8 @@ def main():
                     "h2d_bytes_per_step": (E * N * world) if args.policy == "guided" else 0,
                     "d2h_bytes_per_step": E * N * 6 * world, "ms_per_step": ms_e / steps,
                     "note": "agv_tick_host: pinned host buffers, H2D of the action tensor + tick + D2H of "
-                            "act/reward/done every step; the D2H of step k overlaps the tick of step k+1"},
+                            "act/reward/done every step; the H2D of step k+1 and the D2H of step k-1 overlap the tick "
+                            "of step k (double-buffered device copies, library-owned copy streams)"},
             "gpu_launches": int(launches),
             "clocks": clk,
             # algorithmic bytes per AGV-step: obs record + AGV record r/w + action + reward + done

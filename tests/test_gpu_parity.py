@@ -548,3 +548,67 @@ def test_tick_host_equals_tick(pkg):
     ha, aa = a.get_state(); hb, ab = b.get_state()
     assert np.array_equal(ha, hb) and np.array_equal(aa, ab)
     a.close(); b.close()
+
+
+def _random_layout(rng, H, W):
+    """random track / storage / picking codes with an aisle structure (every storage cell touches a
+    track), row 0 and column 0 kept as track so that the spawn cell (1,1) is free"""
+    g = np.zeros((H, W), dtype=np.uint8)
+    for r in range(2, H - 1):
+        for cc in range(2, W - 1):
+            if (r % 3 != 0) and (cc % (2 + int(rng.integers(2, 6)))) != 0 and rng.random() < 0.8:
+                g[r, cc] = 1
+    for cc in rng.choice(np.arange(2, W - 1), size=min(4, W - 3), replace=False):
+        g[H - 1, cc] = 2
+    return g
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_cross_implementation_fuzz(pkg, seed, monkeypatch):
+    """random map sizes (so that every (NW, RPL) kernel variant, scene counts that do not fill a warp and
+    AGV counts from 1 to 64 occur), random open-loop / guided actions in both protocols, with and without
+    next_obs: the three fused-tick implementations must produce identical outputs and scene states"""
+    import torch
+    rng = np.random.default_rng(1000 + seed)
+    H, W = [(40, 40), (64, 64), (33, 100), (100, 40), (128, 128), (65, 65), (34, 34), (48, 70), (64, 30), (90, 90),
+            (36, 128), (128, 36)][seed]
+    grid = _random_layout(rng, H, W)
+    stor = np.argwhere(grid == 1); pick = np.argwhere(grid == 2)
+    E = int(rng.integers(1, 70)); N = int(rng.choice([1, 2, 7, 33, 64])); T = int(rng.integers(3, 40))
+    tasks = np.zeros((E, T, 4), dtype=np.uint8)
+    for e in range(E):
+        s = stor[rng.integers(0, len(stor), size=T)]; p = pick[rng.integers(0, len(pick), size=T)]
+        tasks[e, :, 0] = s[:, 1] + 1; tasks[e, :, 1] = s[:, 0] + 1; tasks[e, :, 2] = p[:, 1] + 1; tasks[e, :, 3] = p[:, 0] + 1
+    proto = int(seed % 2)
+    policy = [pkg.POLICY_GIVEN, pkg.POLICY_GUIDED, pkg.POLICY_ASTAR][seed % 3]
+    want_next = bool(seed % 4 == 1)
+    results = {}
+    for impl in ("warp", "lanes", "async"):
+        monkeypatch.setenv("AGV_TICK_IMPL", impl)
+        sc = pkg.BatchedScene(grid, E, N, tasks=tasks, P=3, auto_reset=True)
+        sc.reset()
+        arng = np.random.default_rng(77 + seed)
+        trace = []
+        for t in range(60):
+            given = None
+            if policy == pkg.POLICY_GIVEN:
+                given = arng.choice(np.array([-1, -1, -1, -1, -1, 0, 1, 2, 3, 4], dtype=np.int8), size=(E, N))
+            o = sc.tick(proto, policy, pkg.OBS_CLIP, actions=given, want_next=want_next)
+            act = o["act"].cpu().numpy()
+            took = act >= 0
+            rec = [act.copy(), o["reward"].cpu().numpy().copy(), o["done"].cpu().numpy().copy(),
+                   (o["plen"].cpu().numpy().astype(np.int32) & 0xFFFF)[took], o["obs"].float().cpu().numpy()[took]]
+            if want_next:
+                rec.append(o["next_obs"].float().cpu().numpy()[took])
+            trace.append(rec)
+        hdr, agv = sc.get_state()
+        results[impl] = (trace, hdr, agv)
+        sc.close()
+    ref = results["warp"]
+    for impl in ("lanes", "async"):
+        tr, hdr, agv = results[impl]
+        for t, (a, b) in enumerate(zip(ref[0], tr)):
+            for q, (x, y) in enumerate(zip(a, b)):
+                assert np.array_equal(x, y), (impl, seed, t, q)
+        assert np.array_equal(ref[1], hdr) and np.array_equal(ref[2], agv), (impl, seed)
+    assert sum(int((r[0] >= 0).sum()) for r in ref[0]) > 0
