@@ -130,8 +130,8 @@ int lanes_tick(const DevCfg &dc, int NW, int RPL, const LaneArgs &t, cudaStream_
     if (NW == 1 && RPL == 2) {
 #ifdef AGV_LANES_TUNE
         const char *e = getenv("AGV_LANES_SPW"), *w = getenv("AGV_LANES_NWK");
-        const int spw = e ? atoi(e) : 8, nwk = w ? atoi(w) : 0;
-        if (spw == 32 && nwk == 3) return dispatch_obs<1, 2, 32, 3>(dc, t, st);
+        const int spw = e ? atoi(e) : 32, nwk = w ? atoi(w) : 3;
+        if (spw == 8 && nwk == 0) return dispatch_obs<1, 2, 8, 0>(dc, t, st);
         if (spw == 32 && nwk == 2) return dispatch_obs<1, 2, 32, 2>(dc, t, st);
         if (spw == 16 && nwk == 3) return dispatch_obs<1, 2, 16, 3>(dc, t, st);
         if (spw == 16 && nwk == 2) return dispatch_obs<1, 2, 16, 2>(dc, t, st);
@@ -140,7 +140,7 @@ int lanes_tick(const DevCfg &dc, int NW, int RPL, const LaneArgs &t, cudaStream_
         if (spw == 16) return dispatch_obs<1, 2, 16, 0>(dc, t, st);
         if (spw == 32) return dispatch_obs<1, 2, 32, 0>(dc, t, st);
 #endif
-        return dispatch_obs<1, 2, 8, 0>(dc, t, st);
+        return dispatch_obs<1, 2, 32, 3>(dc, t, st);  // shaped reward at 64 x 64: 1.25 ms vs 1.74 ms with <8, 0>
     }
     if (NW == 1 && RPL == 4) return dispatch_obs<1, 4, 32, 0>(dc, t, st);
     if (NW == 2 && RPL == 1) return dispatch_obs<2, 1, 32, 0>(dc, t, st);
