@@ -75,7 +75,9 @@ class BatchedAgent:
         self._train_net = self.policy_network
         if ddp:
             from torch.nn.parallel import DistributedDataParallel
-            self._train_net = DistributedDataParallel(self.policy_network, device_ids=[scene.device_index])
+            self._train_net = DistributedDataParallel(self.policy_network, device_ids=[scene.device_index],
+                                                      broadcast_buffers=False, gradient_as_bucket_view=True,
+                                                      static_graph=True)
         self.epsilon_start = self.epsilon = epsilon
         self.epsilon_end, self.epsilon_count = 1.0, 0
         self.memory_size, self.batch_size = memory_size, batch_size
