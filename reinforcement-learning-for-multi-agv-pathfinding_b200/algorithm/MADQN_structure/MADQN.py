@@ -19,9 +19,9 @@ environment side is the CUDA path:
     agv_end_tick
 
 The CNN is the only dense contraction and stays in PyTorch (bf16 autocast, tensor cores); the
-learner step is captured into one CUDA graph (single-GPU; the DDP learner runs eagerly).
-Multi-GPU: scenes and replay shard per rank; DistributedDataParallel all-reduces the gradients
-over NCCL.  Known reference defect kept out of the data: a guidance STOP (action 4) cannot
+learner step is captured into CUDA graphs (two graphs around the gradient all-reduce with several ranks).
+Multi-GPU: scenes and replay shard per rank; the flattened gradient is all-reduced (mean) over NCCL
+once per update.  Known reference defect kept out of the data: a guidance STOP (action 4) cannot
 index the 4-wide Q row (IndexError in MADQN.py:118), so STOP transitions are not stored.
 """
 from __future__ import annotations
@@ -74,11 +74,15 @@ class BatchedAgent:
         self.target_network = (target_net or Net()).to(self.device).to(memory_format=torch.channels_last)
         self.target_network.load_state_dict(self.policy_network.state_dict())
         self._train_net = self.policy_network
+        self.world = 1
         if ddp:
-            from torch.nn.parallel import DistributedDataParallel
-            self._train_net = DistributedDataParallel(self.policy_network, device_ids=[scene.device_index],
-                                                      broadcast_buffers=False, gradient_as_bucket_view=True,
-                                                      static_graph=True)
+            # data-parallel learner without the DDP wrapper (its hooks cannot be captured): same initial
+            # weights on every rank, one all-reduce of the flattened gradient per update, mean over ranks
+            import torch.distributed as dist
+            self.world = dist.get_world_size()
+            for q in self.policy_network.parameters():
+                dist.broadcast(q.data, src=0)
+            self.target_network.load_state_dict(self.policy_network.state_dict())
         self.epsilon_start = self.epsilon = epsilon
         self.epsilon_end, self.epsilon_count = 1.0, 0
         self.memory_size, self.batch_size = memory_size, batch_size
@@ -95,10 +99,16 @@ class BatchedAgent:
         self._sums = [torch.zeros_like(p) for p in self._params]
         self.loss_function = nn.SmoothL1Loss()
         # the learner step (PER sample -> DDQN target -> SmoothL1 -> backward -> Adagrad) is ~150 tiny
-        # kernels: replayed from one CUDA graph (2.5 ms of launch overhead -> ~0.4 ms).  DDP keeps the
-        # eager path (its gradient hooks do not go into a capture).
-        self.graph_learner = (not ddp) if graph_learner is None else (graph_learner and not ddp)
+        # kernels: replayed from CUDA graphs (2.5 ms of launch overhead -> ~1 ms of GPU work).  With
+        # several ranks it is two graphs around one NCCL all-reduce of the flat gradient.
+        self.graph_learner = True if graph_learner is None else bool(graph_learner)
         self._graph = None
+        self._graph_b = None
+        self._flat = torch.zeros(sum(q.numel() for q in self._params), device=self.device)
+        self._views, off = [], 0
+        for q in self._params:
+            self._views.append(self._flat[off:off + q.numel()].view_as(q))
+            off += q.numel()
         self._warm = 0
         self._u = torch.zeros(batch_size, dtype=torch.float64, device=self.device)
         self._sb = self.memory._alloc_batch(batch_size)
@@ -157,15 +167,18 @@ class BatchedAgent:
     # ------------------------------------------------------------------ learning
     @torch.no_grad()
     def _adagrad_step(self):
-        grads = [p.grad for p in self._params]
+        """torch.optim.Adagrad's update on the (rank-averaged) gradient held in the flat buffer"""
+        grads = self._views
+        if self.world > 1:
+            torch._foreach_div_(grads, float(self.world))
         torch._foreach_addcmul_(self._sums, grads, grads, value=1.0)
         std = torch._foreach_sqrt(self._sums)
         torch._foreach_add_(std, self.adagrad_eps)
         torch._foreach_addcdiv_(self._params, grads, std, value=-self.lr)
 
-    def _learn_body(self):
-        """MADQN.py:134-171 on a device-sampled batch (everything here is capturable: kernel launches
-        on the current stream and tensor ops on static buffers)"""
+    def _backward_body(self):
+        """MADQN.py:134-171 on a device-sampled batch up to the gradient (everything here is capturable:
+        kernel launches on the current stream and tensor ops on static buffers)"""
         b = self._sb
         p = lambda t: t.data_ptr()
         L.check(self.memory.lib.agv_replay_sample(self.memory._h, self.batch_size, p(self._u), p(b["slot"]), p(b["prio"]),
@@ -185,8 +198,19 @@ class BatchedAgent:
                 expected = next_state_values * self.GAMMA * not_done + batch_r
         loss = self.loss_function(state_action_values, expected)
         loss.backward()
-        self._adagrad_step()
+        with torch.no_grad():
+            torch._foreach_copy_(self._views, [q.grad for q in self._params])
         self._loss.copy_(loss.detach())
+
+    def _learn_once(self):
+        """gradient -> [all-reduce] -> Adagrad, eagerly"""
+        for q in self._params:
+            q.grad = None
+        self._backward_body()
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self._flat)
+        self._adagrad_step()
 
     def update_network(self):
         """one optimiser step; the first three run eagerly (warm-up on a side stream), then the step is
@@ -197,28 +221,42 @@ class BatchedAgent:
         self._u.copy_(torch.rand(self.batch_size, dtype=torch.float64, device=self.device, generator=self.gen))
         if self._graph is not None:
             self._graph.replay()
+            if self.world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(self._flat)
+                self._graph_b.replay()
         elif not self.graph_learner:
-            for q in self._params:
-                q.grad = None
-            self._learn_body()
+            self._learn_once()
         elif self._warm < 3:
             self._warm += 1
             cur = torch.cuda.current_stream(self.device)
             side = torch.cuda.Stream(self.device)
             side.wait_stream(cur)
             with torch.cuda.stream(side):
-                for q in self._params:
-                    q.grad = None
-                self._learn_body()
+                self._learn_once()
             cur.wait_stream(side)
         else:
             for q in self._params:
                 q.grad = None
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._learn_body()
-            self._graph = g
-            g.replay()  # the capture itself does not execute the step
+            if self.world == 1:
+                with torch.cuda.graph(g):
+                    self._backward_body()
+                    self._adagrad_step()
+                self._graph = g
+                g.replay()  # the capture itself does not execute the step
+            else:
+                import torch.distributed as dist
+                gb = torch.cuda.CUDAGraph()
+                # thread-local capture mode: the NCCL watchdog thread polls events meanwhile
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    self._backward_body()
+                with torch.cuda.graph(gb, capture_error_mode="thread_local"):
+                    self._adagrad_step()
+                self._graph, self._graph_b = g, gb
+                g.replay()
+                dist.all_reduce(self._flat)
+                gb.replay()
         loss = self._loss.clone()
         self.loss_value.append(loss)
         return loss
