@@ -72,6 +72,33 @@ def test_bfs_fixtures(pkg):
     assert n == len(cases)
 
 
+def test_bfs_fixtures_at_baseline_sizes(pkg):
+    """agv_bfs_batch against the live reference's FindPathAstar at 64x64 / 128x128
+    (tests/golden/bfs_large.json)"""
+    cases = golden("bfs_large.json")
+    by_shape = {}
+    for c in cases:
+        v = np.array([[int(ch) for ch in row] for row in c["valid"]], dtype=np.uint8)
+        by_shape.setdefault(v.shape, []).append((v, c))
+    assert set(by_shape) == {(64, 64), (128, 128)}
+    for shape, lst in by_shape.items():
+        valid = np.stack([v for v, _ in lst])
+        start = np.array([c["start"] for _, c in lst], dtype=np.int32)
+        target = np.array([c["target"] for _, c in lst], dtype=np.int32)
+        act, ln, fnd = pkg.bfs_batch(valid, start, target)
+        act, ln, fnd = act.cpu().numpy(), ln.cpu().numpy(), fnd.cpu().numpy()
+        dist = pkg.bfs_field(valid, target).cpu().numpy()
+        for k, (_, c) in enumerate(lst):
+            first = c["actions"][0] if c["actions"] else 4
+            assert act[k] == first and ln[k] == len(c["actions"]) and bool(fnd[k]) == c["found"], c["name"]
+            # the distance field decreases by one along the reference's whole action list
+            x, y = c["start"]
+            for j, a in enumerate(c["actions"]):
+                dx, dy = [(0, -1), (1, 0), (0, 1), (-1, 0)][a]
+                x, y = x + dx, y + dy
+                assert dist[k, y, x] == len(c["actions"]) - 1 - j, (c["name"], j)
+
+
 @pytest.mark.parametrize("H,W", [(9, 9), (32, 32), (33, 64), (64, 64), (64, 65), (20, 128), (65, 40), (128, 128),
                                   (1, 7), (7, 1), (128, 3)])
 def test_bfs_random_vs_oracle(pkg, H, W):

@@ -26,6 +26,31 @@ def test_bfs_matches_reference_fixtures():
         assert a_l == first and a_f == first
 
 
+def _large_cases():
+    for c in golden("bfs_large.json"):
+        v = np.array([[int(ch) for ch in row] for row in c["valid"]], dtype=np.uint8)
+        yield c, v
+
+
+def test_bfs_matches_reference_fixtures_at_baseline_sizes():
+    """63 FindPathAstar runs of the live reference at 64x64 (bench workload c3 matrices with
+    AGV obstacles, random grids, walls) and 128x128 (c5): closes the parity chain
+    reference -> literal restatement -> distance-field rule at BASELINE sizes."""
+    n64 = n128 = 0
+    for c, v in _large_cases():
+        assert v.shape == (c["H"], c["W"])
+        a_l, f_l, acts = orc.bfs_literal(v, c["start"], c["target"])
+        a_f, f_f, ln = orc.bfs_field(v, c["start"], c["target"])
+        assert f_l == c["found"] and f_f == c["found"], c["name"]
+        assert acts == c["actions"], c["name"]
+        assert ln == len(c["actions"]), c["name"]
+        first = c["actions"][0] if c["actions"] else 4
+        assert a_l == first and a_f == first, c["name"]
+        n64 += c["H"] == 64
+        n128 += c["H"] == 128
+    assert n64 >= 50 and n128 >= 5
+
+
 def test_bfs_field_equals_literal_large_grids():
     rng = np.random.default_rng(5)
     for n in range(60):
