@@ -213,6 +213,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--shaped", action="store_true", help="settings.Sparse_Reward shaped reward (a second path search per turn)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--rollout", type=int, default=0, help="ticks per step: one agv_rollout launch of that many ticks")
     args = ap.parse_args()
     steps, warmup = max(1, args.steps), max(3, args.warmup)
 
@@ -391,7 +392,10 @@ def main():
         return 0
 
     def step():
-        sc.tick(PROTO, POL, OBS, want_lens=False, out=out)
+        if args.rollout > 0:
+            sc.rollout(args.rollout, PROTO, POL, OBS, want_lens=False, out=out)
+        else:
+            sc.tick(PROTO, POL, OBS, want_lens=False, out=out)
 
     spin = args.spinup if args.spinup >= 0 else 2 * N
     for _ in range(spin):

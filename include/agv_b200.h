@@ -131,6 +131,28 @@ int agv_tick_host(AgvHandle *h, int32_t proto, int32_t policy, int32_t obs_kind,
                   void *obs_dev, void *next_obs_dev, void *stream);
 int agv_tick_host_join(AgvHandle *h, void *stream);
 
+/* ---- multi-tick rollout ------------------------------------------------------
+ * n_ticks passes of the while-loop body of Scene.run_mode (Scene.py:111-164) for every scene in ONE
+ * launch: exactly the results of n_ticks consecutive agv_tick calls with the same proto / policy /
+ * obs_kind, written to rings indexed [tick, scene, agv]:
+ *   action_dev [n_ticks,E,N] (POLICY_GIVEN: open-loop actions, negative = A* guidance),
+ *   act_out / reward / done / plen / slen [n_ticks,E,N], obs / next_obs bf16 [n_ticks,E,N,3,K,K].
+ * This is Scene.run_game("A_star") / Expert.create_data_by_self (ExpertManager.py:35-52) and the
+ * A*-guided branch of AG-DQN (MADQN.py:96-111 with u >= epsilon) for E scenes at once: no network is
+ * in the loop, so a scene never has to wait for the other scenes between its ticks.  Scenes are
+ * scheduled heaviest-first (by the BFS count of their last tick) onto persistent CTAs.  Inside a
+ * written group of 8 observation records, records of AGVs without a turn are zero-filled; mask with
+ * act_out >= 0 as for agv_tick.  Configurations the persistent kernel does not cover (shaped reward,
+ * full-map observations, K != 7) run as n_ticks fused ticks -- same results. */
+int agv_rollout(AgvHandle *h, int32_t n_ticks, int32_t proto, int32_t policy, int32_t obs_kind,
+                const int8_t *action_dev, int8_t *act_out_dev, float *reward_dev, uint8_t *done_dev,
+                uint16_t *plen_dev, uint16_t *slen_dev, void *obs_dev, void *next_obs_dev, void *stream);
+/* Same with HOST (pinned) buffers for the [n_ticks,E,N] actions in and act / reward / done out;
+ * double-buffered and overlapped like agv_tick_host; agv_tick_host_join waits for the copy-backs. */
+int agv_rollout_host(AgvHandle *h, int32_t n_ticks, int32_t proto, int32_t policy, int32_t obs_kind,
+                     const int8_t *action_host, int8_t *act_out_host, float *reward_host, uint8_t *done_host,
+                     void *obs_dev, void *next_obs_dev, void *stream);
+
 /* ---- sub-step protocol (NN in the loop) -------------------------------------
  * The callback protocol of Scene.py:144-158 split into tensor calls per AGV index k:
  *   agv_begin_tick; for k in 0..N-1: agv_encode(k) -> policy -> agv_step_turn(k)

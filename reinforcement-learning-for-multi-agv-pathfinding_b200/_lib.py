@@ -35,6 +35,8 @@ SYMBOLS = {
     "agv_tick": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "agv_tick_host": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "agv_tick_host_join": (C.c_int, [_vp, _vp]),
+    "agv_rollout": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "agv_rollout_host": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "agv_begin_tick": (C.c_int, [_vp, _vp]),
     "agv_encode": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "agv_bfs_action": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp]),

@@ -157,6 +157,61 @@ class BatchedScene:
         """The current stream waits for the outstanding copy-backs of tick_host."""
         L.check(self.lib.agv_tick_host_join(self._h, self._stream()), "agv_tick_host_join")
 
+    # ------------------------------------------------------------------ multi-tick rollout
+    def rollout(self, n_ticks: int, proto, policy, obs_kind=L.OBS_NONE, actions=None, want_next=False,
+                want_lens=True, out=None):
+        """n_ticks Scene.run_mode loop passes for every scene in one launch (agv_rollout): the same
+        results as n_ticks calls of tick(), in rings indexed [tick, scene, agv].  `actions`
+        (POLICY_GIVEN) is an open-loop [n_ticks, E, N] int8 tensor (negative = A* guidance)."""
+        K, E, N = int(n_ticks), self.E, self.N
+        o = {} if out is None else out
+        o.setdefault("act", self._get("r_act%d" % K, (K, E, N), torch.int8))
+        o.setdefault("reward", self._get("r_reward%d" % K, (K, E, N), torch.float32))
+        o.setdefault("done", self._get("r_done%d" % K, (K, E, N), torch.uint8))
+        if want_lens:
+            o.setdefault("plen", self._get("r_plen%d" % K, (K, E, N), torch.int16))
+            o.setdefault("slen", self._get("r_slen%d" % K, (K, E, N), torch.int16))
+        if obs_kind != L.OBS_NONE:
+            shp = (K, E, N) + self.obs_shape(obs_kind)
+            o.setdefault("obs", self._get("r_obs%d_%d" % (obs_kind, K), shp, torch.bfloat16))
+            if want_next:
+                o.setdefault("next_obs", self._get("r_next%d_%d" % (obs_kind, K), shp, torch.bfloat16))
+        a = None
+        if policy == L.POLICY_GIVEN:
+            a = torch.as_tensor(actions, device=self.device).to(torch.int8).contiguous()
+            assert tuple(a.shape) == (K, E, N)
+        L.check(self.lib.agv_rollout(self._h, K, proto, policy, obs_kind, _ptr(a), _ptr(o["act"]), _ptr(o["reward"]),
+                                     _ptr(o["done"]), _ptr(o.get("plen")), _ptr(o.get("slen")), _ptr(o.get("obs")),
+                                     _ptr(o.get("next_obs")), self._stream()), "agv_rollout")
+        return o
+
+    def rollout_host(self, n_ticks: int, proto, policy, obs_kind=L.OBS_NONE, actions_host=None, want_next=False,
+                     join=True):
+        """rollout() through HOST (pinned) buffers: [n_ticks, E, N] actions in, act / reward / done out
+        (agv_rollout_host); observations stay on the device."""
+        K, E, N = int(n_ticks), self.E, self.N
+        hb = self._buf.setdefault("host_r%d" % K, {})
+        if not hb:
+            hb["act"] = torch.empty((K, E, N), dtype=torch.int8).pin_memory()
+            hb["reward"] = torch.empty((K, E, N), dtype=torch.float32).pin_memory()
+            hb["done"] = torch.empty((K, E, N), dtype=torch.uint8).pin_memory()
+        obs = nxt = None
+        if obs_kind != L.OBS_NONE:
+            shp = (K, E, N) + self.obs_shape(obs_kind)
+            obs = self._get("r_obs%d_%d" % (obs_kind, K), shp, torch.bfloat16)
+            if want_next:
+                nxt = self._get("r_next%d_%d" % (obs_kind, K), shp, torch.bfloat16)
+        ah = None
+        if policy == L.POLICY_GIVEN:
+            ah = actions_host
+            assert ah.dtype == torch.int8 and tuple(ah.shape) == (K, E, N) and ah.is_contiguous()
+        L.check(self.lib.agv_rollout_host(self._h, K, proto, policy, obs_kind, _ptr(ah), _ptr(hb["act"]),
+                                          _ptr(hb["reward"]), _ptr(hb["done"]), _ptr(obs), _ptr(nxt), self._stream()),
+                "agv_rollout_host")
+        if join:
+            self.host_join()
+        return {"act": hb["act"], "reward": hb["reward"], "done": hb["done"], "obs": obs, "next_obs": nxt}
+
     def collect_expert(self, replay, n_ticks: int, obs_kind=L.OBS_CLIP):
         """Expert-mode rollout collection (ExpertManager.create_data_by_self, batched): `n_ticks`
         passes of the A_star control mode for every scene; each AGV turn's (state, A* action)

@@ -12,8 +12,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libagv_b200.so")
-SOURCES = ["agv_kernels.cu", "agv_lanes.cu", "agv_replay.cu"]
-HEADERS = ["agv_core.cuh", "agv_lanes.cuh", "agv_async.cuh", os.path.join("..", "..", "include", "agv_b200.h")]
+SOURCES = ["agv_kernels.cu", "agv_lanes.cu", "agv_rollout.cu", "agv_replay.cu"]
+HEADERS = ["agv_core.cuh", "agv_lanes.cuh", "agv_async.cuh", "agv_rollout.cuh", os.path.join("..", "..", "include", "agv_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 OBJ_DIR = os.path.join(HERE, "build")

@@ -1,6 +1,6 @@
 // agv_kernels.cu -- kernels + C ABI (include/agv_b200.h) of the batched scene.
 // sm_100a only.  See agv_core.cuh for the warp-per-scene device core.
-#include "agv_lanes.cuh"
+#include "agv_rollout.cuh"
 #include "../../include/agv_b200.h"
 
 #include <atomic>
@@ -13,6 +13,7 @@
 namespace agv {
 
 int lanes_tick(const DevCfg &dc, int NW, int RPL, const LaneArgs &t, cudaStream_t st, int allow_async);  // agv_lanes.cu
+int lanes_rollout(const DevCfg &dc, int NW, int RPL, const RollArgs &ra, unsigned *order, cudaStream_t st);  // agv_rollout.cu
 
 static std::atomic<uint64_t> g_launches{0};
 static const char *g_tick_kernel = "none";
@@ -355,6 +356,16 @@ struct AgvHandle {
     bool copy_pending[2] = {false, false};
     unsigned host_calls = 0;
     std::vector<uint8_t> h_state;
+    // persistent rollout (agv_rollout): heaviest-first scene order + queue counter, packed-window scratch
+    // rings of the record writer, and double-buffered result rings for agv_rollout_host
+    unsigned *d_order = nullptr, *d_qctr = nullptr;
+    unsigned long long *d_scr[2] = {nullptr, nullptr};
+    size_t scr_cap[2] = {0, 0};
+    int8_t *r_action[2] = {nullptr, nullptr}, *r_act_out[2] = {nullptr, nullptr};
+    float *r_reward[2] = {nullptr, nullptr};
+    uint8_t *r_done[2] = {nullptr, nullptr};
+    size_t r_cap = 0;
+    unsigned roll_calls = 0;
 };
 
 static inline int align16(int x) { return (x + 15) & ~15; }
@@ -404,11 +415,12 @@ static int warps_per_cta() {
 //   * full-map observations are HBM-write-bound and best written by a whole warp per scene;
 //   * maps up to 32 x 32 have short searches and few scenes per SM: warp-per-scene;
 //   * everything else runs lane-per-scene (decoupled lanes where agv_async.cuh covers it).
-static int tick_impl(const AgvHandle *h, int obs_kind) {  // 0 warp, 1 lanes, 2 async
+static int tick_impl(const AgvHandle *h, int obs_kind) {  // 0 warp, 1 lanes, 2 async, 3 rollout
     const char *e = getenv("AGV_TICK_IMPL");
     if (e && strcmp(e, "warp") == 0) return 0;
     if (e && strcmp(e, "lanes") == 0) return 1;
     if (e && strcmp(e, "async") == 0) return 2;
+    if (e && strcmp(e, "rollout") == 0) return 3;  // the persistent rollout kernel with n_ticks = 1
     if (obs_kind == AGV_OBS_FULL) return 0;
     if (h->NW == 1 && h->RPL == 1) return 0;
     return 2;
@@ -447,6 +459,60 @@ static int obs_elems(const AgvHandle *h, int obs_kind) {
     if (obs_kind == AGV_OBS_CLIP) return 3 * h->dc.K * h->dc.K;
     if (obs_kind == AGV_OBS_FULL) return 3 * h->cfg.H * h->cfg.W;
     return 0;
+}
+
+// library-owned copy streams + events of the *_host entry points (created on first use)
+static cudaError_t host_streams(AgvHandle *h) {
+    if (h->copy_stream) return cudaSuccess;
+    cudaError_t e;
+    for (int b = 0; b < 2; b++) {
+        if ((e = cudaEventCreateWithFlags(&h->ev_tick[b], cudaEventDisableTiming)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&h->ev_copy[b], cudaEventDisableTiming)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&h->ev_h2d[b], cudaEventDisableTiming)) != cudaSuccess) return e;
+    }
+    if ((e = cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    return cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+}
+
+// Launch of the persistent rollout kernel (agv_rollout.cuh) for n_ticks ticks; AGV_E_UNSUPPORTED when
+// the configuration is outside what that kernel covers (the caller then loops over agv_tick).
+static int rollout_launch(AgvHandle *h, int n_ticks, int proto, int policy, int obs_kind, const int8_t *action_dev,
+                          int8_t *act_out_dev, float *reward_dev, uint8_t *done_dev, uint16_t *plen_dev,
+                          uint16_t *slen_dev, void *obs_dev, void *next_obs_dev, cudaStream_t st) {
+    const DevCfg &d = h->dc;
+    const size_t per_tick = (size_t)d.E * d.N, n = per_tick * (size_t)n_ticks;
+    if (n >= (1ull << 31)) return AGV_E_UNSUPPORTED;
+    if (d.shaped || !(obs_kind == AGV_OBS_NONE || (obs_kind == AGV_OBS_CLIP && d.K == 7))) return AGV_E_UNSUPPORTED;
+    if (!h->d_order) {
+        CUDA_TRY(cudaMalloc(&h->d_order, sizeof(unsigned) * (size_t)d.E));
+        CUDA_TRY(cudaMalloc(&h->d_qctr, sizeof(unsigned)));
+    }
+    void *obs_p[2] = {obs_dev, next_obs_dev};
+    for (int b = 0; b < 2; b++)
+        if (obs_p[b] && h->scr_cap[b] < n) {
+            if (h->d_scr[b]) { CUDA_TRY(cudaStreamSynchronize(st)); CUDA_TRY(cudaFree(h->d_scr[b])); h->d_scr[b] = nullptr; h->scr_cap[b] = 0; }
+            CUDA_TRY(cudaMalloc(&h->d_scr[b], n * sizeof(unsigned long long)));
+            h->scr_cap[b] = n;
+        }
+    RollArgs ra; memset(&ra, 0, sizeof(ra));
+    LaneArgs &la = ra.la;
+    la.proto = proto; la.policy = policy; la.obs_kind = obs_kind;
+    la.action = action_dev; la.act_out = act_out_dev; la.reward = reward_dev; la.done = done_dev;
+    la.plen = plen_dev; la.slen = slen_dev; la.obs = (uint16_t *)obs_dev; la.next_obs = (uint16_t *)next_obs_dev;
+    la.rec_elems = obs_elems(h, obs_kind);
+    ra.K = n_ticks;
+    ra.scr_obs = h->d_scr[0]; ra.scr_next = h->d_scr[1];
+    ra.qctr = h->d_qctr;
+    ra.vec_ok = (d.N % 8 == 0) && (((uintptr_t)obs_dev | (uintptr_t)next_obs_dev) & 15) == 0;
+    // per-AGV outputs default to "no turn" (the kernel only writes the turns that happen)
+    if (act_out_dev) CUDA_TRY(cudaMemsetAsync(act_out_dev, 0xFF, n, st));
+    if (done_dev) CUDA_TRY(cudaMemsetAsync(done_dev, 0, n, st));
+    if (reward_dev) CUDA_TRY(cudaMemsetAsync(reward_dev, 0, n * sizeof(float), st));
+    if (plen_dev) CUDA_TRY(cudaMemsetAsync(plen_dev, 0, n * sizeof(uint16_t), st));
+    if (slen_dev) CUDA_TRY(cudaMemsetAsync(slen_dev, 0xFF, n * sizeof(uint16_t), st));
+    const int rc = lanes_rollout(d, h->NW, h->RPL, ra, h->d_order, st);
+    if (rc == 0) g_tick_kernel = "k_rollout (persistent lane-per-scene rollout, heaviest-first scene queue)";
+    return rc;
 }
 
 extern "C" {
@@ -521,6 +587,11 @@ int agv_destroy(AgvHandle *h) {
     }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
+    cudaFree(h->d_order); cudaFree(h->d_qctr);
+    for (int b = 0; b < 2; b++) {
+        cudaFree(h->d_scr[b]);
+        cudaFree(h->r_action[b]); cudaFree(h->r_act_out[b]); cudaFree(h->r_reward[b]); cudaFree(h->r_done[b]);
+    }
     delete h;
     return AGV_OK;
 }
@@ -567,14 +638,19 @@ int agv_tick(AgvHandle *h, int32_t proto, int32_t policy, int32_t obs_kind, cons
     const int N = h->cfg.N;
     t.rec_elems = obs_elems(h, t.obs_kind);
     const int impl = tick_impl(h, t.obs_kind);
+    if (impl == 3) {
+        const int rc = rollout_launch(h, 1, proto, policy, t.obs_kind, action_dev, act_out_dev, reward_dev, done_dev,
+                                      plen_dev, slen_dev, obs_dev, next_obs_dev, (cudaStream_t)stream);
+        if (rc != AGV_E_UNSUPPORTED) return rc;
+    }
     if (impl > 0) {
         LaneArgs la; memset(&la, 0, sizeof(la));
         la.proto = t.proto; la.policy = t.policy; la.obs_kind = t.obs_kind;
         la.action = t.action; la.act_out = t.act_out; la.reward = t.reward; la.done = t.done;
         la.plen = t.plen; la.slen = t.slen; la.obs = t.obs; la.next_obs = t.next_obs; la.rec_elems = t.rec_elems;
-        const int rc = lanes_tick(h->dc, h->NW, h->RPL, la, (cudaStream_t)stream, impl == 2);
+        const int rc = lanes_tick(h->dc, h->NW, h->RPL, la, (cudaStream_t)stream, impl >= 2);
         if (rc != AGV_E_UNSUPPORTED) {
-            const bool as = impl == 2 && !h->dc.shaped && (t.obs_kind == AGV_OBS_NONE || (t.obs_kind == AGV_OBS_CLIP && h->dc.K == 7));
+            const bool as = impl >= 2 && !h->dc.shaped && (t.obs_kind == AGV_OBS_NONE || (t.obs_kind == AGV_OBS_CLIP && h->dc.K == 7));
             g_tick_kernel = as ? "k_tick_async (lane-per-scene, decoupled lanes + BFS worker warps)"
                                : "k_tick_lanes (lane-per-scene, lock step)";
             return rc;
@@ -620,19 +696,15 @@ int agv_tick_host(AgvHandle *h, int32_t proto, int32_t policy, int32_t obs_kind,
     if (!h) return AGV_E_INVALID;
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     const size_t n = (size_t)h->cfg.E * h->cfg.N;
-    if (!h->copy_stream) {
+    if (!h->d_action[0]) {
         for (int b = 0; b < 2; b++) {
             CUDA_TRY(cudaMalloc(&h->d_action[b], n));
             CUDA_TRY(cudaMalloc(&h->d_act_out[b], n));
             CUDA_TRY(cudaMalloc(&h->d_reward[b], n * sizeof(float)));
             CUDA_TRY(cudaMalloc(&h->d_done[b], n));
-            CUDA_TRY(cudaEventCreateWithFlags(&h->ev_tick[b], cudaEventDisableTiming));
-            CUDA_TRY(cudaEventCreateWithFlags(&h->ev_copy[b], cudaEventDisableTiming));
-            CUDA_TRY(cudaEventCreateWithFlags(&h->ev_h2d[b], cudaEventDisableTiming));
         }
-        CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-        CUDA_TRY(cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
     }
+    CUDA_TRY(host_streams(h));
     cudaStream_t st = (cudaStream_t)stream;
     const int b = h->host_calls & 1;
     // the tick overwrites result buffer b: the copy-back of the call before last must be out
@@ -666,6 +738,85 @@ int agv_tick_host_join(AgvHandle *h, void *stream) {
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     for (int b = 0; b < 2; b++)
         if (h->copy_pending[b]) CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, h->ev_copy[b], 0));
+    return AGV_OK;
+}
+
+int agv_rollout(AgvHandle *h, int32_t n_ticks, int32_t proto, int32_t policy, int32_t obs_kind,
+                const int8_t *action_dev, int8_t *act_out_dev, float *reward_dev, uint8_t *done_dev,
+                uint16_t *plen_dev, uint16_t *slen_dev, void *obs_dev, void *next_obs_dev, void *stream) {
+    if (!h || n_ticks < 0 || proto < 0 || proto > 1 || policy < 0 || policy > 2 || obs_kind < 0 || obs_kind > 2)
+        return AGV_E_INVALID;
+    if (obs_kind == AGV_OBS_NONE && (obs_dev || next_obs_dev)) return AGV_E_INVALID;
+    if (n_ticks == 0) return AGV_OK;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const int ok = (obs_dev || next_obs_dev) ? obs_kind : AGV_OBS_NONE;
+    const char *e = getenv("AGV_ROLLOUT_IMPL");  // "ticks" forces the per-tick fallback (A/B runs, tests)
+    if (!(e && strcmp(e, "ticks") == 0)) {
+        const int rc = rollout_launch(h, n_ticks, proto, policy, ok, action_dev, act_out_dev, reward_dev, done_dev,
+                                      plen_dev, slen_dev, obs_dev, next_obs_dev, (cudaStream_t)stream);
+        if (rc != AGV_E_UNSUPPORTED) return rc;
+    }
+    // configurations the persistent kernel does not cover (shaped reward, full-map observations,
+    // K != 7): n_ticks launches of the fused tick, each writing its slice of the rings
+    const size_t per = (size_t)h->cfg.E * h->cfg.N, R = (size_t)obs_elems(h, ok);
+    for (int k = 0; k < n_ticks; k++) {
+        const size_t o = per * (size_t)k;
+        const int rc = agv_tick(h, proto, policy, obs_kind, action_dev ? action_dev + o : nullptr,
+                                act_out_dev ? act_out_dev + o : nullptr, reward_dev ? reward_dev + o : nullptr,
+                                done_dev ? done_dev + o : nullptr, plen_dev ? plen_dev + o : nullptr,
+                                slen_dev ? slen_dev + o : nullptr, obs_dev ? (uint16_t *)obs_dev + o * R : nullptr,
+                                next_obs_dev ? (uint16_t *)next_obs_dev + o * R : nullptr, stream);
+        if (rc != AGV_OK) return rc;
+    }
+    return AGV_OK;
+}
+
+int agv_rollout_host(AgvHandle *h, int32_t n_ticks, int32_t proto, int32_t policy, int32_t obs_kind,
+                     const int8_t *action_host, int8_t *act_out_host, float *reward_host, uint8_t *done_host,
+                     void *obs_dev, void *next_obs_dev, void *stream) {
+    if (!h || n_ticks < 1) return AGV_E_INVALID;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const size_t n = (size_t)h->cfg.E * h->cfg.N * (size_t)n_ticks;
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(host_streams(h));
+    if (h->r_cap < n) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        for (int b = 0; b < 2; b++) {
+            cudaFree(h->r_action[b]); cudaFree(h->r_act_out[b]); cudaFree(h->r_reward[b]); cudaFree(h->r_done[b]);
+            h->r_action[b] = h->r_act_out[b] = nullptr; h->r_reward[b] = nullptr; h->r_done[b] = nullptr;
+            CUDA_TRY(cudaMalloc(&h->r_action[b], n));
+            CUDA_TRY(cudaMalloc(&h->r_act_out[b], n));
+            CUDA_TRY(cudaMalloc(&h->r_reward[b], n * sizeof(float)));
+            CUDA_TRY(cudaMalloc(&h->r_done[b], n));
+        }
+        h->r_cap = n;
+        h->copy_pending[0] = h->copy_pending[1] = false;
+        h->tick_pending[0] = h->tick_pending[1] = false;
+    }
+    // same double-buffered pipeline as agv_tick_host: the upload of call k+1 and the copy-back of call
+    // k-1 overlap the rollout of call k
+    const int b = h->roll_calls & 1;
+    if (h->copy_pending[b]) CUDA_TRY(cudaStreamWaitEvent(st, h->ev_copy[b], 0));
+    if (policy == AGV_POLICY_GIVEN) {
+        if (!action_host) return AGV_E_INVALID;
+        if (h->tick_pending[b]) CUDA_TRY(cudaStreamWaitEvent(h->h2d_stream, h->ev_tick[b], 0));
+        CUDA_TRY(cudaMemcpyAsync(h->r_action[b], action_host, n, cudaMemcpyHostToDevice, h->h2d_stream));
+        CUDA_TRY(cudaEventRecord(h->ev_h2d[b], h->h2d_stream));
+        CUDA_TRY(cudaStreamWaitEvent(st, h->ev_h2d[b], 0));
+    }
+    const int rc = agv_rollout(h, n_ticks, proto, policy, obs_kind, policy == AGV_POLICY_GIVEN ? h->r_action[b] : nullptr,
+                               h->r_act_out[b], h->r_reward[b], h->r_done[b], nullptr, nullptr, obs_dev, next_obs_dev,
+                               stream);
+    if (rc != AGV_OK) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev_tick[b], st));
+    h->tick_pending[b] = true;
+    CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_tick[b], 0));
+    if (act_out_host) CUDA_TRY(cudaMemcpyAsync(act_out_host, h->r_act_out[b], n, cudaMemcpyDeviceToHost, h->copy_stream));
+    if (reward_host) CUDA_TRY(cudaMemcpyAsync(reward_host, h->r_reward[b], n * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
+    if (done_host) CUDA_TRY(cudaMemcpyAsync(done_host, h->r_done[b], n, cudaMemcpyDeviceToHost, h->copy_stream));
+    CUDA_TRY(cudaEventRecord(h->ev_copy[b], h->copy_stream));
+    h->copy_pending[b] = true;
+    h->roll_calls++;
     return AGV_OK;
 }
 

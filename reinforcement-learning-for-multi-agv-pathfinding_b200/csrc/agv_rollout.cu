@@ -1,0 +1,123 @@
+// agv_rollout.cu -- kernels + launcher of the persistent multi-tick rollout (agv_rollout.cuh).
+// sm_100a only.  Called from agv_rollout / agv_tick (agv_kernels.cu).
+#include "agv_rollout.cuh"
+
+#include <cstdlib>
+
+namespace agv {
+void note_launch();
+void note_cuda_error(int e);
+
+template <int NW, int RPL>
+constexpr int rollout_min_ctas() { return NW * RPL <= 2 ? 4 : (NW * RPL <= 4 ? 2 : 1); }
+
+template <int NW, int RPL, int OBS, int SPW, int NB>
+__global__ void __launch_bounds__(32 * (2 + NB + (OBS == OBS_CLIP ? 1 : 0)), rollout_min_ctas<NW, RPL>())
+k_rollout(const DevCfg c, const RollArgs ra) {
+    extern __shared__ __align__(16) uint8_t lane_smem[];
+    rollout_cta<NW, RPL, OBS, SPW, NB>(c, ra, lane_smem);
+}
+
+// Heaviest-first scene order: counting sort of the scenes by the BFS count of their last tick (scene
+// header word 6, clipped to 63), heaviest bucket first.  One CTA; the order inside a bucket does not
+// matter (scenes are independent: the schedule never changes a result).
+__global__ void __launch_bounds__(1024) k_rollout_order(const DevCfg c, unsigned *order, unsigned *qctr, unsigned q0) {
+    __shared__ unsigned hist[64], base[64];
+    if (threadIdx.x < 64) hist[threadIdx.x] = 0u;
+    __syncthreads();
+    for (int e = threadIdx.x; e < c.E; e += blockDim.x) {
+        const unsigned w = *reinterpret_cast<const unsigned *>(c.state + (size_t)e * c.env_stride + 24);
+        atomicAdd(&hist[63u - min(w, 63u)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned s = 0;
+        for (int b = 0; b < 64; b++) { base[b] = s; s += hist[b]; }
+        *qctr = q0;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < c.E; e += blockDim.x) {
+        const unsigned w = *reinterpret_cast<const unsigned *>(c.state + (size_t)e * c.env_stride + 24);
+        order[atomicAdd(&base[63u - min(w, 63u)], 1u)] = (unsigned)e;
+    }
+}
+
+static inline int align8r(int x) { return (x + 7) & ~7; }
+
+template <int NW, int SPW>
+static int plan_rollout(const DevCfg &dc, LaneArgs &t) {
+    const int HN = dc.H * NW;
+    int off = 0;
+    t.off_tab = off; off += (mirror_copy<NW>() ? 4 : 2) * HN * 8;
+    t.blk_stride = dc.env_stride + 4;  // odd number of words: same-field accesses of the 32 lanes hit 32 banks
+    t.off_blk = off; off = align8r(off + SPW * t.blk_stride);
+    t.occ_stride = HN | 1;
+    t.off_occ = off; off += SPW * t.occ_stride * 8;
+    t.off_occm = off; off += mirror_copy<NW>() ? SPW * t.occ_stride * 8 : 0;
+    t.off_vrow = off;
+    t.off_zero = off; off += HN * 8;
+    t.off_queue = (off + 15) & ~15; off = t.off_queue + (int)sizeof(RollShared);
+    return off;
+}
+
+static int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+template <int NW, int RPL, int OBS, int SPW, int NB>
+static int launch_rollout(const DevCfg &dc, RollArgs ra, unsigned *order, cudaStream_t st) {
+    const int smem = plan_rollout<NW, SPW>(dc, ra.la);
+    auto kern = k_rollout<NW, RPL, OBS, SPW, NB>;
+    const int threads = 32 * (2 + NB + (OBS == OBS_CLIP ? 1 : 0));
+    if (smem > 227 * 1024) return -4;  // AGV_E_UNSUPPORTED
+    static int cps_cached = 0, sms = 0, smem_cached = -1;  // per template instance (one device per process)
+    if (smem != smem_cached) {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) { note_cuda_error((int)e); return -2; }
+        }
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        int dev = 0, n = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, smem);
+        if (e != cudaSuccess || n < 1) { note_cuda_error((int)e); return -2; }
+        cps_cached = n;
+        smem_cached = smem;
+    }
+    // persistent CTAs: at most `cps` per SM (AGV_ROLLOUT_CPS lowers it: fewer resident scenes, each running
+    // faster, the rest waiting in the queue), never more than the scenes need
+    int cps = env_int("AGV_ROLLOUT_CPS", 0);
+    if (cps < 1 || cps > cps_cached) cps = cps_cached;
+    int ctas = (dc.E + SPW - 1) / SPW;
+    if (ctas > sms * cps) ctas = sms * cps;
+    k_rollout_order<<<1, 1024, 0, st>>>(dc, order, ra.qctr, (unsigned)ctas * SPW);
+    note_launch();
+    ra.order = order;
+    kern<<<ctas, threads, smem, st>>>(dc, ra);
+    note_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { note_cuda_error((int)e); return -2; }
+    return 0;
+}
+
+template <int NW, int RPL>
+static int dispatch_rollout(const DevCfg &dc, const RollArgs &ra, unsigned *order, cudaStream_t st) {
+    if (ra.la.obs_kind == OBS_CLIP) return launch_rollout<NW, RPL, OBS_CLIP, 32, 3>(dc, ra, order, st);
+    return launch_rollout<NW, RPL, OBS_NONE, 32, 3>(dc, ra, order, st);
+}
+
+// covers no-observation and 3x7x7 limited-visual rollouts without the shaped reward; everything else
+// returns AGV_E_UNSUPPORTED and the caller falls back to n_ticks launches of agv_tick
+int lanes_rollout(const DevCfg &dc, int NW, int RPL, const RollArgs &ra, unsigned *order, cudaStream_t st) {
+    if (dc.shaped || !(ra.la.obs_kind == OBS_NONE || (ra.la.obs_kind == OBS_CLIP && dc.K == 7))) return -4;
+    if (NW == 1 && RPL == 1) return dispatch_rollout<1, 1>(dc, ra, order, st);
+    if (NW == 1 && RPL == 2) return dispatch_rollout<1, 2>(dc, ra, order, st);
+    if (NW == 1 && RPL == 4) return dispatch_rollout<1, 4>(dc, ra, order, st);
+    if (NW == 2 && RPL == 1) return dispatch_rollout<2, 1>(dc, ra, order, st);
+    if (NW == 2 && RPL == 2) return dispatch_rollout<2, 2>(dc, ra, order, st);
+    return dispatch_rollout<2, 4>(dc, ra, order, st);
+}
+
+}  // namespace agv

@@ -1,0 +1,537 @@
+// agv_rollout.cuh -- persistent multi-tick rollout: every scene runs n_ticks passes of
+// Scene.run_mode's loop body (Scene.py:111-164) inside ONE kernel launch.
+//
+// In A_star / Expert mode and in the A*-guided branch of AG-DQN the scenes are independent across
+// ticks as well as inside one, so the per-tick launch of agv_tick is only a barrier: it makes every
+// tick as long as its most congested scene.  Here a lane keeps its scene for all n_ticks (its own
+// tick counter next to its own turn cursor, same decoupled-lane state machine as agv_async.cuh),
+// outputs go to [n_ticks, E, N, ...] rings, and CTAs are persistent: when a scene has finished its
+// n_ticks the slot is handed to a BFS worker warp, which writes the scene block back, takes the next
+// scene from a global queue (heaviest first -- ordered by the BFS count of the scene's last tick)
+// and loads it.  Long scenes start first and short ones fill in behind them.
+//
+// Warp roles in a CTA:  warp 0 / 1       scene warps: the slots whose last tick was light / heavy
+//                                        (a slot migrates between them at tick boundaries)
+//                       warps 2..NB+1    BFS workers: level-synchronous BFS requests + slot swaps
+//                       warp NB+2        record writer (OBS_CLIP): turns the packed 49-bit windows
+//                                        of a finished scene-tick into [3,7,7] bf16 records with
+//                                        16-byte stores (8 records = 147 uint4, always aligned)
+// Results are bit-identical to n_ticks calls of agv_tick (tests/test_gpu_rollout.py).
+#pragma once
+#include "agv_async.cuh"
+
+namespace agv {
+
+constexpr int ROLL_RING = 32;  // tick-end record requests in flight per scene warp
+
+struct RollArgs {
+    LaneArgs la;              // proto / policy / obs kind, tick-0 base pointers, shared-memory plan
+    int K;                    // ticks per scene
+    int vec_ok;               // N % 8 == 0 and 16-byte aligned rings: vector-store path
+    unsigned long long *scr_obs, *scr_next;  // [K*E*N] packed window records (wm | tpos << 49)
+    const unsigned *order;    // [E] scene indices, heaviest first
+    unsigned *qctr;           // next entry of `order` to hand out
+};
+
+struct RollShared {
+    unsigned bfs_state[32];   // per slot: 0 idle, 1 BFS posted, 2 taken, 3 answered, 4 swap posted, 5 swap taken
+    unsigned bfs_req[32];
+    unsigned bfs_res[32];
+    unsigned ctl[32];         // 0 / 1: running on scene warp 0 / 1; 2 / 3: handed to scene warp 0 / 1; 4: exhausted
+    int slot_e[32];           // scene held by the slot (-1: none)
+    int slot_k[32];           // ticks of the rollout this scene has done
+    unsigned slot_fl[32];     // bit 0: two created AGVs may share a cell (LaneScene::overlap)
+    int exit_flag;
+    unsigned done_warps;
+    unsigned done_slots;      // slots that found the scene queue empty
+    int pad;
+    unsigned enc_head[2], enc_tail[2];
+    uint4 enc_ring[2][ROLL_RING];          // {first record of the scene-tick, acted lo, acted hi, -}
+    unsigned long long recbits[64][3];     // writer staging: the 147-bit strings of one scene-tick's records
+};
+
+constexpr int LS_IDLE = 4, LS_NEWTICK = 5;
+
+// ------------------------------------------------------------------ slot <-> HBM (one warp, coalesced)
+template <int NW>
+__device__ __forceinline__ void roll_store_slot(const DevCfg &c, const LaneArgs &t, uint8_t *smem, int slot, int e,
+                                                int lane) {
+    const int wps = c.env_stride >> 2;
+    uint32_t *dst = reinterpret_cast<uint32_t *>(c.state + (size_t)e * c.env_stride);
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(smem + t.off_blk + (size_t)slot * t.blk_stride);
+    for (int w = lane; w < wps; w += 32) dst[w] = src[w];
+}
+
+// loads scene e into `slot`, builds its occupancy rows and hands it to the scene warp that fits its weight
+template <int NW>
+__device__ __forceinline__ void roll_load_slot(const DevCfg &c, const LaneArgs &t, uint8_t *smem, RollShared *sh,
+                                               int slot, int e, int lane) {
+    constexpr int WB = 64 * NW;
+    const int wps = c.env_stride >> 2, HN = c.H * NW;
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(c.state + (size_t)e * c.env_stride);
+    uint32_t *blk = reinterpret_cast<uint32_t *>(smem + t.off_blk + (size_t)slot * t.blk_stride);
+    {
+        uint32_t v[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) { const int w = lane + 32 * q; v[q] = w < wps ? __ldg(src + w) : 0u; }
+#pragma unroll
+        for (int q = 0; q < 4; q++) { const int w = lane + 32 * q; if (w < wps) blk[w] = v[q]; }
+    }
+    uint64_t *occ = reinterpret_cast<uint64_t *>(smem + t.off_occ) + (size_t)slot * t.occ_stride;
+    uint64_t *occm = reinterpret_cast<uint64_t *>(smem + t.off_occm) + (size_t)slot * t.occ_stride;
+    for (int q = lane; q < HN; q += 32) { occ[q] = 0ull; if (mirror_copy<NW>()) occm[q] = 0ull; }
+    __syncwarp();
+    const int n_created = (int)(blk[3] & 0xFFFFu);
+    const uint16_t *pos = reinterpret_cast<const uint16_t *>(reinterpret_cast<const uint8_t *>(blk) + c.off_pos);
+    for (int j = lane; j < n_created; j += 32) {
+        const int p = pos[j], x0 = (p & 255) - 1, y0 = (p >> 8) - 1;
+        atomicOr(reinterpret_cast<unsigned *>(occ) + y0 * NW * 2 + (x0 >> 5), 1u << (x0 & 31));
+        if (mirror_copy<NW>()) {
+            const int xm = WB - 1 - x0;
+            atomicOr(reinterpret_cast<unsigned *>(occm) + y0 * NW * 2 + (xm >> 5), 1u << (xm & 31));
+        }
+    }
+    __syncwarp();
+    int bits = 0;
+    for (int q = lane; q < HN; q += 32) bits += __popcll(occ[q]);
+    bits = __reduce_add_sync(FULL, bits);
+    if (lane == 0) {
+        sh->slot_e[slot] = e;
+        sh->slot_k[slot] = 0;
+        sh->slot_fl[slot] = bits != n_created ? 1u : 0u;
+        const unsigned heavy = blk[6] >= (unsigned)AGV_HEAVY_BFS ? 1u : 0u;
+        __threadfence_block();
+        *reinterpret_cast<volatile unsigned *>(&sh->ctl[slot]) = 2u + heavy;
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------ BFS worker (+ slot swaps)
+template <int NW, int RPL, int SPW>
+__device__ __forceinline__ void roll_worker(const DevCfg &c, const RollArgs &ra, uint8_t *smem) {
+    const LaneArgs &t = ra.la;
+    const int lane = threadIdx.x & 31, HN = c.H * NW;
+    RollShared *sh = reinterpret_cast<RollShared *>(smem + t.off_queue);
+    volatile unsigned *vs = sh->bfs_state;
+    volatile int *vexit = &sh->exit_flag;
+    const uint64_t *tab = reinterpret_cast<const uint64_t *>(smem + t.off_tab);
+    const uint64_t *occ0 = reinterpret_cast<const uint64_t *>(smem + t.off_occ);
+    for (;;) {
+        const unsigned s = vs[lane];
+        unsigned m = __ballot_sync(FULL, s == 1u || s == 4u);
+        if (!m) {
+            if (*vexit) return;
+            __nanosleep(AGV_POLL_NS);
+            continue;
+        }
+        int j = -1;
+        unsigned kind = 0;
+        while (m) {
+            const int k = __ffs(m) - 1;
+            m &= m - 1;
+            const unsigned sk = __shfl_sync(FULL, s, k);
+            int ok = 0;
+            if (lane == 0) ok = atomicCAS(&sh->bfs_state[k], sk, sk + 1u) == sk;
+            ok = __shfl_sync(FULL, ok, 0);
+            if (ok) { j = k; kind = sk; break; }
+        }
+        if (j < 0) continue;
+        __threadfence_block();
+        if (kind == 1u) {
+            const unsigned pk = *reinterpret_cast<volatile unsigned *>(&sh->bfs_req[j]);
+            int bl = 0;
+            const int ba = coop_bfs<NW, RPL>(pk, tab, HN, occ0 + (size_t)j * t.occ_stride, c.H, c.W, lane, bl);
+            if (lane == 0) {
+                *reinterpret_cast<volatile unsigned *>(&sh->bfs_res[j]) = (unsigned)ba | ((unsigned)bl << 8);
+                __threadfence_block();
+                vs[j] = 3u;
+            }
+        } else {
+            // the scene of slot j has done its n_ticks: write it back, take the next one from the queue
+            const int old = *reinterpret_cast<volatile int *>(&sh->slot_e[j]);
+            if (old >= 0) roll_store_slot<NW>(c, t, smem, j, old, lane);
+            unsigned idx = 0;
+            if (lane == 0) idx = atomicAdd(ra.qctr, 1u);
+            idx = __shfl_sync(FULL, idx, 0);
+            __syncwarp();
+            if (lane == 0) vs[j] = 0u;
+            if (idx < (unsigned)c.E) {
+                roll_load_slot<NW>(c, t, smem, sh, j, (int)__ldg(ra.order + idx), lane);
+            } else if (lane == 0) {
+                sh->slot_e[j] = -1;
+                *reinterpret_cast<volatile unsigned *>(&sh->ctl[j]) = 4u;
+                __threadfence_block();
+                atomicAdd(&sh->done_slots, 1u);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------ record writer
+// One finished scene-tick: the packed windows of its AGVs (scr, written by the scene lane turn by
+// turn) become [3,7,7] bf16 records.  A record is a 147-bit string (49 bits per channel); 8 records
+// are 1176 bits = 147 x 8 bits, and 8 bits expand to one uint4 of bf16 -- so with N % 8 == 0 every
+// store is a full, aligned 16-byte vector.  Records of AGVs without a turn inside a written group
+// are zero-filled (the consumer masks with act_out >= 0, as for agv_tick).
+__device__ __forceinline__ void roll_expand(const RollArgs &ra, RollShared *sh, uint16_t *dst,
+                                            const unsigned long long *scr, unsigned rec_base, uint64_t acted, int lane) {
+    if (!acted) return;
+    const int n_hi = 64 - __clzll((long long)acted);
+    const int G = (n_hi + 7) >> 3;
+    if (!ra.vec_ok) {
+        for (int r = 0; r < n_hi; r++) {
+            if (!((acted >> r) & 1ull)) continue;
+            const unsigned long long m = __ldcg(scr + rec_base + r);
+            expand_clip7(dst + ((size_t)rec_base + r) * 147, m & ((1ull << 49) - 1ull), (int)((m >> 49) & 63ull), lane);
+        }
+        return;
+    }
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        const int r = lane + 32 * q;
+        if (r < 8 * G) {
+            const bool valid = (acted >> r) & 1ull;
+            const unsigned long long m = valid ? __ldcg(scr + rec_base + r) : 0ull;
+            const unsigned long long wm = m & ((1ull << 49) - 1ull);
+            const int tp = (int)((m >> 49) & 63ull);
+            unsigned long long w0 = 0ull, w1 = 0ull, w2 = 0ull;
+            if (valid) {
+                w0 = (1ull << 24) | (tp < 15 ? (1ull << (49 + tp)) : 0ull);
+                w1 = (tp >= 15 ? (1ull << (tp - 15)) : 0ull) | (wm << 34);
+                w2 = wm >> 30;
+            }
+            sh->recbits[r][0] = w0; sh->recbits[r][1] = w1; sh->recbits[r][2] = w2;
+        }
+    }
+    __syncwarp();
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst + (size_t)rec_base * 147);
+    const int nv = G * 147;
+    for (int v = lane; v < nv; v += 32) {
+        const unsigned bit = 8u * (unsigned)v;
+        const unsigned r = bit / 147u, off = bit - r * 147u;
+        const unsigned wi = off >> 6, sft = off & 63u;
+        unsigned long long lo = sh->recbits[r][wi] >> sft;
+        if (sft && wi < 2u) lo |= sh->recbits[r][wi + 1] << (64u - sft);
+        // (bits past the end of record r are bits 0..6 of record r+1's first channel: always zero)
+        const unsigned bits = (unsigned)lo & 0xFFu;
+        uint4 o;
+        unsigned u, w;
+        u = bits & 3u;        w = (u | (u << 15)) & 0x10001u; o.x = w * (unsigned)BF16_ONE;
+        u = (bits >> 2) & 3u; w = (u | (u << 15)) & 0x10001u; o.y = w * (unsigned)BF16_ONE;
+        u = (bits >> 4) & 3u; w = (u | (u << 15)) & 0x10001u; o.z = w * (unsigned)BF16_ONE;
+        u = (bits >> 6) & 3u; w = (u | (u << 15)) & 0x10001u; o.w = w * (unsigned)BF16_ONE;
+        d4[v] = o;
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void roll_writer(const RollArgs &ra, uint8_t *smem) {
+    const LaneArgs &t = ra.la;
+    const int lane = threadIdx.x & 31;
+    RollShared *sh = reinterpret_cast<RollShared *>(smem + t.off_queue);
+    volatile unsigned *vhead = sh->enc_head, *vtail = sh->enc_tail;
+    volatile int *vexit = &sh->exit_flag;
+    unsigned mine[2] = {0u, 0u};
+    for (;;) {
+        bool any = false;
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const unsigned h = vhead[q];
+            if (h == mine[q]) continue;
+            any = true;
+            __threadfence_block();
+            for (; mine[q] != h; mine[q]++) {
+                const uint4 rq = sh->enc_ring[q][mine[q] % ROLL_RING];
+                const uint64_t acted = (uint64_t)rq.y | ((uint64_t)rq.z << 32);
+                if (t.obs) roll_expand(ra, sh, t.obs, ra.scr_obs, rq.x, acted, lane);
+                if (t.next_obs) roll_expand(ra, sh, t.next_obs, ra.scr_next, rq.x, acted, lane);
+            }
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) vtail[q] = mine[q];
+        }
+        if (any) continue;
+        if (*vexit) {  // the last requests are posted before the exit flag
+            if (vhead[0] == mine[0] && vhead[1] == mine[1]) return;
+            continue;
+        }
+        __nanosleep(AGV_POLL_NS);
+    }
+}
+
+// ------------------------------------------------------------------ scene warp
+template <int NW, int RPL, int OBS, int SPW>
+__device__ __forceinline__ void roll_scene_warp(const DevCfg &c, const RollArgs &ra, uint8_t *smem, const int which) {
+    const LaneArgs &t = ra.la;
+    const int lane = threadIdx.x & 31;
+    LaneScene<NW, RPL, SPW, 0> ws(c, t, smem, lane, 0);
+    RollShared *sh = reinterpret_cast<RollShared *>(smem + t.off_queue);
+    volatile unsigned *vs = sh->bfs_state, *vctl = sh->ctl;
+    volatile unsigned *vdone_slots = &sh->done_slots;
+    volatile unsigned *vhead = &sh->enc_head[which], *vtail = &sh->enc_tail[which];
+    const int N = c.N, K = ra.K;
+    const uint64_t om_a = N > 1 ? ~0ull : 0ull;
+    const bool want_obs = OBS == OBS_CLIP && t.obs != nullptr, want_next = OBS == OBS_CLIP && t.next_obs != nullptr;
+    const uint64_t *zr = reinterpret_cast<const uint64_t *>(smem + t.off_zero);
+    ws.has = false; ws.e = 0; ws.tasks_e = c.tasks;
+    ws.over = 1; ws.finished = 0; ws.n_created = 0; ws.tick = 0; ws.cursor = 0; ws.n_done = 0; ws.acted_mask = 0;
+
+    int st = LS_IDLE, i = 0, n_loop = 0, k = 0;
+    unsigned n_bfs = 0;     // BFS searches of the tick in progress (weight of the scene once the tick is over)
+    unsigned rec0 = 0;      // (k * E + e) * N: first output record of the scene's tick in progress
+    unsigned head = 0;
+    Agv a;
+    a.x = a.y = a.tx = a.ty = 1; a.stage = a.loaded = a.idle = a.order = 0;
+    int action = -1, plen = 0, given = -1;
+    int pf_idx = -1, pf_val = -1;
+    bool guard = false;
+
+    for (;;) {
+        if (*vdone_slots >= (unsigned)SPW) break;  // every slot of the CTA has found the queue empty
+        const bool pick = st == LS_IDLE && vctl[lane] == 2u + (unsigned)which;
+        if (!__any_sync(FULL, pick || st == LS_NEWTICK || st == LS_START || st == LS_HAVE ||
+                                  (st == LS_WAIT && vs[lane] == 3u))) {
+            __nanosleep(100);
+            continue;
+        }
+        // ---- 0: slots handed to this warp (freshly loaded by a worker, or migrated from the other scene warp)
+        if (pick) {
+            __threadfence_block();
+            ws.hdr_to_regs();
+            ws.e = *reinterpret_cast<volatile int *>(&sh->slot_e[lane]);
+            ws.tasks_e = c.tasks + (size_t)ws.e * c.T;
+            k = *reinterpret_cast<volatile int *>(&sh->slot_k[lane]);
+            ws.overlap = (*reinterpret_cast<volatile unsigned *>(&sh->slot_fl[lane]) & 1u) != 0u;
+            n_bfs = ws.hdr_w[6];
+            vctl[lane] = (unsigned)which;
+            st = LS_NEWTICK;
+        }
+        // ---- 1: tick boundary
+        if (st == LS_NEWTICK) {
+            const int w_new = n_bfs >= (unsigned)AGV_HEAVY_BFS ? 1 : 0;
+            if (k >= K) {          // this scene is through: a worker stores it and fetches the next one
+                ws.regs_to_hdr(); ws.hdr_w[6] = n_bfs;
+                __threadfence_block();
+                vs[lane] = 4u;
+                st = LS_IDLE;
+            } else if (w_new != which) {  // its last tick was heavy (light): continue on the other scene warp
+                ws.regs_to_hdr(); ws.hdr_w[6] = n_bfs;
+                sh->slot_k[lane] = k; sh->slot_fl[lane] = ws.overlap ? 1u : 0u;
+                __threadfence_block();
+                vctl[lane] = 2u + (unsigned)w_new;
+                st = LS_IDLE;
+            } else {
+                bool live = true;
+                if (ws.over) {
+                    if (c.auto_reset) {  // Scene.init: every AGV back at (1,1), AGV 0 created
+                        ws.reset();
+                        for (int q = 0; q < ws.HN; q++) { ws.occ[q] = 0ull; if (mirror_copy<NW>()) ws.occm[q] = 0ull; }
+                        ws.occ_set(0, 0);
+                        ws.overlap = false;
+                    } else live = false;
+                }
+                if (!live) k = K;  // a finished episode without auto-reset: the remaining ticks do nothing
+                else {
+                    ws.tick++; ws.acted_mask = 0;
+                    i = 0; n_loop = min(N, ws.n_created); n_bfs = 0; pf_idx = -1;
+                    rec0 = ((unsigned)k * (unsigned)c.E + (unsigned)ws.e) * (unsigned)N;
+                    st = LS_START;
+                }
+            }
+        }
+        // ---- A: answers of the BFS workers
+        if (st == LS_WAIT && vs[lane] == 3u) {
+            __threadfence_block();
+            const unsigned r = *reinterpret_cast<volatile unsigned *>(&sh->bfs_res[lane]);
+            vs[lane] = 0u;
+            action = (int)(r & 0xFFu); plen = (int)(r >> 8);
+            if (guard) { ws.occ_clear(0, 0); guard = false; }
+            st = LS_HAVE;
+        }
+        // ---- B: finish the turn of the lanes that have their action
+        // (Explorer.check_action, Explorer.py:151-208; Scene.py:155-158)
+        const bool fin = st == LS_HAVE;
+        if (fin) {
+            const bool guided = (t.policy == POLICY_GUIDED) || (t.policy == POLICY_GIVEN && given < 0);
+            const bool pol_a = !guided && t.policy == POLICY_ASTAR;
+            if (!guided && !pol_a && action > A_STOP) { ws.cnt_bad++; action = A_STOP; }
+            const int dx = (action == A_RIGHT) - (action == A_LEFT);
+            const int dy = (action == A_DOWN) - (action == A_UP);
+            const int nx = a.x + dx, ny = a.y + dy;
+            int r = 0, end = 0;
+            const bool oob = nx < 1 || ny < 1 || nx > c.W || ny > c.H;
+            if (oob) { r = -1; end = 1; }
+            else {
+                const int code = ws.cell_code(nx - 1, ny - 1);
+                const bool at_target = (nx == a.tx) && (ny == a.ty);
+                if (code == 1 && a.loaded && !at_target) { r = -1; end = 1; }
+                else if (code == 2 && !at_target) { r = -1; end = 1; }
+                else if (t.proto == PROTO_INTELLIGENT && ws.other_at_from(i, nx | (ny << 8), a.x | (a.y << 8))) { r = -1; end = 1; }
+                else if (at_target) { r = 1; ws.continue_working(a); }
+            }
+            // Explorer.py:145-148: the move is applied iff not is_end
+            if (t.proto != PROTO_INTELLIGENT && !guided && !pol_a) ws.overlap = true;
+            if (!end && (dx | dy)) {
+                const bool still = ws.other_at_from(i, a.x | (a.y << 8), a.x | (a.y << 8));
+                ws.occ_move(a.x - 1, a.y - 1, nx - 1, ny - 1, !still);
+                a.x = nx; a.y = ny;
+            }
+            ws.store_agv(i, a);
+            if (t.proto == PROTO_INTELLIGENT) {
+                if (ws.finished || (long long)ws.tick >= c.max_steps) end = 1;  // Scene.py:155
+                if (end) ws.over = 1;
+            } else {
+                end = 0;  // is_end is ignored in A_star / manual mode (Scene.py:159-162)
+            }
+            ws.acted_mask |= (1ull << i);
+            ws.cnt_turns++;
+            ws.cnt_ended += end;
+            const size_t rec = (size_t)rec0 + i;
+            if (t.act_out) t.act_out[rec] = (int8_t)action;
+            if (t.done) t.done[rec] = (uint8_t)end;
+            if (t.reward) t.reward[rec] = (float)r;
+            if (t.plen) t.plen[rec] = (uint16_t)plen;
+            if (want_next) {  // store_info's create_state on the snapshot after the move (Scene.py:156)
+                bool shared = false;
+                if (ws.overlap) shared = ws.other_at(i, a.x | (a.y << 8));
+                const uint64_t wm = lane_window7<NW>(ws.tab + a.loaded * ws.HN, ws.occ, c.H, a.x - 1, a.y - 1, a.tx - 1,
+                                                     a.ty - 1, shared);
+                const int tpos = (max(-3, min(3, a.ty - a.y)) + 3) * 7 + max(-3, min(3, a.tx - a.x)) + 3;
+                ra.scr_next[rec] = wm | ((unsigned long long)tpos << 49);
+            }
+            i++;
+            st = LS_START;
+        }
+        // ---- C: start the next turn (Scene.py:124-134 skip rules first) -- or end the tick
+        bool tick_end = false;
+        if (st == LS_START) {
+            for (;;) {
+                if (i >= n_loop || ws.over) { tick_end = true; break; }
+                if (ws.finished) { ws.over = 1; ws.cnt_ended++; tick_end = true; break; }  // Scene.py:129-130
+                if (!((ws.meta_s[i] >> 3) & 1)) break;                                      // idle AGVs are skipped
+                i++;
+            }
+        }
+        if (tick_end) {
+            if (!ws.over) ws.spawn();  // Scene.check_new_veh, Scene.py:164
+            k++;
+            st = LS_NEWTICK;
+        }
+        if (want_obs || want_next) {
+            // the finished scene-ticks go to the record writer: {first record, who took a turn}
+            const bool post = tick_end && ws.acted_mask != 0ull;
+            const unsigned pend = __ballot_sync(FULL, post);
+            if (pend) {
+                const int n = __popc(pend);
+                while ((int)(head + (unsigned)n - *vtail) > ROLL_RING) __nanosleep(40);
+                if (post)
+                    sh->enc_ring[which][(head + (unsigned)__popc(pend & ((1u << lane) - 1u))) % ROLL_RING] =
+                        make_uint4(rec0, (unsigned)ws.acted_mask, (unsigned)(ws.acted_mask >> 32), 0u);
+                __threadfence_block();  // also orders the lane's packed-window stores before the request
+                __syncwarp();
+                head += (unsigned)n;
+                if (lane == 0) *vhead = head;
+            }
+        }
+        const bool act = st == LS_START;
+        uint64_t wm_obs = ~0ull;
+        if (act) {
+            a = ws.load_agv(i);
+            given = -1;
+            if (t.policy == POLICY_GIVEN && t.action) {
+                // the action of the next AGV index was requested a turn ago (a global load here would
+                // put ~500 cycles of latency on every turn of the scene's chain)
+                given = (pf_idx == i) ? pf_val : (int)t.action[(size_t)rec0 + i];
+                pf_idx = i + 1;
+                pf_val = (i + 1 < N) ? (int)t.action[(size_t)rec0 + i + 1] : -1;
+            }
+            if (want_obs) {
+                bool shared = false;
+                if (ws.overlap) shared = ws.other_at(i, a.x | (a.y << 8));
+                wm_obs = lane_window7<NW>(ws.tab + a.loaded * ws.HN, ws.occ, c.H, a.x - 1, a.y - 1, a.tx - 1, a.ty - 1,
+                                          shared);
+                const int tpos = (max(-3, min(3, a.ty - a.y)) + 3) * 7 + max(-3, min(3, a.tx - a.x)) + 3;
+                ra.scr_obs[(size_t)rec0 + i] = wm_obs | ((unsigned long long)tpos << 49);
+            }
+        }
+        if (__any_sync(FULL, act)) {
+            const bool guided = (t.policy == POLICY_GUIDED) || (t.policy == POLICY_GIVEN && given < 0);
+            const bool pol_a = !guided && t.policy == POLICY_ASTAR;
+            bool need = act && (guided || pol_a);
+            if (act && !need) { action = given; plen = 0; st = LS_HAVE; }
+            const int sx = a.x - 1, sy = a.y - 1, tx = a.tx - 1, ty = a.ty - 1;
+            if (need && sx == tx && sy == ty) { action = A_STOP; plen = 0; st = LS_HAVE; need = false; }
+            // boxed in: none of the four neighbour cells is valid in matrix (b) -- they are cells 17, 23,
+            // 25, 31 of the window just extracted -- so FindPathAstar cannot leave the start: STOP, length 0
+            if (need && guided && want_obs && !ws.overlap &&
+                !(wm_obs & ((1ull << 17) | (1ull << 23) | (1ull << 25) | (1ull << 31)))) {
+                action = A_STOP; plen = 0; st = LS_HAVE; need = false;
+            }
+            // matrix (a) also blocks (1,1) while uncreated AGVs park there (Explorer.py:274-283)
+            if (need && pol_a && N > 1 && ws.n_created < N && !ws.occ_test(0, 0)) { ws.occ_set(0, 0); guard = true; }
+            const uint64_t om = guided ? ~0ull : om_a;
+            int l = 0;
+            const int ma = lane_monotone<NW>(need, ws.tab, ws.HN, om ? ws.occ : zr, om ? ws.occm : zr, a.loaded, sx, sy, tx,
+                                             ty, l);
+            if (need) {
+                if (ma >= 0) {
+                    action = ma; plen = l; st = LS_HAVE;
+                    if (guard) { ws.occ_clear(0, 0); guard = false; }
+                } else {  // level-synchronous BFS by a worker warp; this scene waits, the others go on
+                    *reinterpret_cast<volatile unsigned *>(&sh->bfs_req[lane]) =
+                        (unsigned)sx | ((unsigned)sy << 7) | ((unsigned)tx << 14) | ((unsigned)ty << 21) |
+                        ((unsigned)a.loaded << 28) | (om ? (1u << 29) : 0u);
+                    __threadfence_block();
+                    vs[lane] = 1u;
+                    st = LS_WAIT;
+                    n_bfs++;
+                }
+            }
+        }
+    }
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0 && atomicAdd(&sh->done_warps, 1u) == 1u) *reinterpret_cast<volatile int *>(&sh->exit_flag) = 1;
+    {
+        const unsigned ct = __reduce_add_sync(FULL, ws.cnt_turns), ce = __reduce_add_sync(FULL, ws.cnt_ended),
+                       cb = __reduce_add_sync(FULL, ws.cnt_bad);
+        if (lane == 0) {
+            if (ct) atomicAdd(c.counters + 0, (unsigned long long)ct);
+            if (ce) atomicAdd(c.counters + 1, (unsigned long long)ce);
+            if (cb) atomicAdd(c.counters + 2, (unsigned long long)cb);
+        }
+    }
+}
+
+// kernel body: role by warp index
+template <int NW, int RPL, int OBS, int SPW, int NB>
+__device__ __forceinline__ void rollout_cta(const DevCfg &c, const RollArgs &ra, uint8_t *smem) {
+    const LaneArgs &t = ra.la;
+    RollShared *sh = reinterpret_cast<RollShared *>(smem + t.off_queue);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    if (warp == 0) {
+        sh->bfs_state[lane] = 0u; sh->ctl[lane] = 4u; sh->slot_e[lane] = -1; sh->slot_k[lane] = 0; sh->slot_fl[lane] = 0u;
+        if (lane == 0) {
+            sh->exit_flag = 0; sh->done_warps = 0u; sh->done_slots = 0u;
+            sh->enc_head[0] = sh->enc_head[1] = 0u; sh->enc_tail[0] = sh->enc_tail[1] = 0u;
+        }
+    } else if (warp == 1) {
+        LaneScene<NW, RPL, SPW, 0> ws(c, t, smem, lane, 0);
+        ws.load_tables();
+    }
+    __syncthreads();
+    // first fill: slot j of CTA b takes entry b + j * gridDim of the heaviest-first order, so the heavy
+    // scenes are spread over all CTAs; later scenes come from the queue counter (starts at SPW * gridDim)
+    for (int j = warp; j < SPW; j += n_warps) {
+        const unsigned idx = blockIdx.x + (unsigned)j * gridDim.x;
+        if (idx < (unsigned)c.E) roll_load_slot<NW>(c, t, smem, sh, j, (int)__ldg(ra.order + idx), lane);
+        else if (lane == 0) atomicAdd(&sh->done_slots, 1u);
+    }
+    __syncthreads();
+    if (warp < 2) roll_scene_warp<NW, RPL, OBS, SPW>(c, ra, smem, warp);
+    else if (warp < 2 + NB) roll_worker<NW, RPL, SPW>(c, ra, smem);
+    else roll_writer(ra, smem);
+}
+
+}  // namespace agv

@@ -32,10 +32,11 @@ def pkg():
     return load_pkg()
 
 
-@pytest.fixture(params=["async", "lanes", "warp"])
+@pytest.fixture(params=["async", "lanes", "warp", "rollout"])
 def tick_impl(request, monkeypatch):
     """Runs a fused-tick test once per implementation of agv_tick: decoupled lanes
-    (agv_async.cuh, the default), lock-step lanes (agv_lanes.cuh) and warp-per-scene (k_tick).
+    (agv_async.cuh, the default), lock-step lanes (agv_lanes.cuh), warp-per-scene (k_tick) and the
+    persistent rollout kernel with n_ticks = 1 (agv_rollout.cuh).
     The library reads AGV_TICK_IMPL at every call."""
     monkeypatch.setenv("AGV_TICK_IMPL", request.param)
     return request.param

@@ -57,7 +57,7 @@ def test_fullsize_properties_and_sampled_parity(workload, E, ticks, monkeypatch)
     envs = {e: orc.Env(grid, tasks[e], N) for e in sample}
     pool = ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 4))  # the C oracle releases the GIL
     checks = []
-    for rep, impl in enumerate(["async", "warp", "lanes", "async"]):
+    for rep, impl in enumerate(["async", "warp", "lanes", "rollout", "async"]):
         monkeypatch.setenv("AGV_TICK_IMPL", impl)
         sc = pkg.BatchedScene(grid, E, N, tasks=tasks, P=3, auto_reset=True)
         sc.reset()

@@ -594,7 +594,7 @@ def _random_layout(rng, H, W):
 def test_cross_implementation_fuzz(pkg, seed, monkeypatch):
     """random map sizes (so that every (NW, RPL) kernel variant, scene counts that do not fill a warp and
     AGV counts from 1 to 64 occur), random open-loop / guided actions in both protocols, with and without
-    next_obs: the three fused-tick implementations must produce identical outputs and scene states"""
+    next_obs: the four fused-tick implementations must produce identical outputs and scene states"""
     import torch
     rng = np.random.default_rng(1000 + seed)
     H, W = [(40, 40), (64, 64), (33, 100), (100, 40), (128, 128), (65, 65), (34, 34), (48, 70), (64, 30), (90, 90),
@@ -610,7 +610,7 @@ def test_cross_implementation_fuzz(pkg, seed, monkeypatch):
     policy = [pkg.POLICY_GIVEN, pkg.POLICY_GUIDED, pkg.POLICY_ASTAR][seed % 3]
     want_next = bool(seed % 4 == 1)
     results = {}
-    for impl in ("warp", "lanes", "async"):
+    for impl in ("warp", "lanes", "async", "rollout"):
         monkeypatch.setenv("AGV_TICK_IMPL", impl)
         sc = pkg.BatchedScene(grid, E, N, tasks=tasks, P=3, auto_reset=True)
         sc.reset()
@@ -632,7 +632,7 @@ def test_cross_implementation_fuzz(pkg, seed, monkeypatch):
         results[impl] = (trace, hdr, agv)
         sc.close()
     ref = results["warp"]
-    for impl in ("lanes", "async"):
+    for impl in ("lanes", "async", "rollout"):
         tr, hdr, agv = results[impl]
         for t, (a, b) in enumerate(zip(ref[0], tr)):
             for q, (x, y) in enumerate(zip(a, b)):
