@@ -236,6 +236,10 @@ const char *agv_version(void);
 /* name of the kernel the last agv_tick / agv_tick_host call launched (three bit-identical
  * implementations exist; the library picks by shape, AGV_TICK_IMPL=async|lanes|warp forces one) */
 const char *agv_last_tick_kernel(void);
+/* profiling builds only (-DAGV_ROLL_PROF, AGV_ROLL_PROF=1): per-scene timeline of the last agv_rollout,
+ * uint64[E,8] = {finish ns, BFS searches, turns, cycles waiting for BFS answers, start ns, pick-ups,
+ * CTA, sum of BFS path lengths}; AGV_E_UNSUPPORTED otherwise.  Synchronous. */
+int agv_rollout_profile(AgvHandle *h, uint64_t *out_host, void *stream);
 
 #ifdef __cplusplus
 }

@@ -59,6 +59,7 @@ SYMBOLS = {
     "agv_launch_count": (C.c_uint64, []),
     "agv_version": (C.c_char_p, []),
     "agv_last_tick_kernel": (C.c_char_p, []),
+    "agv_rollout_profile": (C.c_int, [_vp, _vp, _vp]),
 }
 
 _lib = None

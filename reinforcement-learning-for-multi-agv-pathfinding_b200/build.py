@@ -40,7 +40,8 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build() and not os.environ.get("AGV_NVCC_EXTRA") and _last_flags() == "":
+    if (not force and not needs_build() and not os.environ.get("AGV_NVCC_EXTRA") and _last_flags() == ""
+            and not os.environ.get("AGV_BUILD_OUT")):
         return LIB
     # one object per translation unit, compiled in parallel and only when stale, then one link
     hdr_t = max(os.path.getmtime(os.path.join(CSRC, h)) for h in HEADERS)
@@ -64,13 +65,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if verbose:
             sys.stderr.write(err)
     objs = [os.path.join(obj_dir, s.replace(".cu", ".o")) for s in SOURCES]
-    r = subprocess.run([_nvcc(), "-shared", "-o", LIB] + objs, capture_output=True, text=True)
+    out = os.environ.get("AGV_BUILD_OUT") or LIB   # tuning variants are linked elsewhere (tuning/mkvariant.sh)
+    r = subprocess.run([_nvcc(), "-shared", "-o", out] + objs, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed linking %s" % LIB)
-    with open(os.path.join(OBJ_DIR, "last_flags"), "w") as f:
-        f.write(" ".join(extra))
-    return LIB
+        raise RuntimeError("nvcc failed linking %s" % out)
+    if out == LIB:
+        with open(os.path.join(OBJ_DIR, "last_flags"), "w") as f:
+            f.write(" ".join(extra))
+    return out
 
 
 def _last_flags() -> str:

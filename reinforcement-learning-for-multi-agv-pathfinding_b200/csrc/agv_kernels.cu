@@ -366,6 +366,7 @@ struct AgvHandle {
     uint8_t *r_done[2] = {nullptr, nullptr};
     size_t r_cap = 0;
     unsigned roll_calls = 0;
+    unsigned long long *d_prof = nullptr;  // -DAGV_ROLL_PROF builds with AGV_ROLL_PROF=1 in the environment
 };
 
 static inline int align16(int x) { return (x + 15) & ~15; }
@@ -487,12 +488,13 @@ static int rollout_launch(AgvHandle *h, int n_ticks, int proto, int policy, int 
         CUDA_TRY(cudaMalloc(&h->d_order, sizeof(unsigned) * (size_t)d.E));
         CUDA_TRY(cudaMalloc(&h->d_qctr, sizeof(unsigned)));
     }
-    void *obs_p[2] = {obs_dev, next_obs_dev};
+    // per-turn scratch records of the scene lanes (agv_rollout.cuh): 16 B per turn, + 8 B with next_obs
+    const size_t need[2] = {n * 2, next_obs_dev ? n : 0};
     for (int b = 0; b < 2; b++)
-        if (obs_p[b] && h->scr_cap[b] < n) {
+        if (h->scr_cap[b] < need[b]) {
             if (h->d_scr[b]) { CUDA_TRY(cudaStreamSynchronize(st)); CUDA_TRY(cudaFree(h->d_scr[b])); h->d_scr[b] = nullptr; h->scr_cap[b] = 0; }
-            CUDA_TRY(cudaMalloc(&h->d_scr[b], n * sizeof(unsigned long long)));
-            h->scr_cap[b] = n;
+            CUDA_TRY(cudaMalloc(&h->d_scr[b], need[b] * sizeof(unsigned long long)));
+            h->scr_cap[b] = need[b];
         }
     RollArgs ra; memset(&ra, 0, sizeof(ra));
     LaneArgs &la = ra.la;
@@ -501,8 +503,15 @@ static int rollout_launch(AgvHandle *h, int n_ticks, int proto, int policy, int 
     la.plen = plen_dev; la.slen = slen_dev; la.obs = (uint16_t *)obs_dev; la.next_obs = (uint16_t *)next_obs_dev;
     la.rec_elems = obs_elems(h, obs_kind);
     ra.K = n_ticks;
-    ra.scr_obs = h->d_scr[0]; ra.scr_next = h->d_scr[1];
+    ra.scr_turn = reinterpret_cast<ulonglong2 *>(h->d_scr[0]); ra.scr_next = h->d_scr[1];
     ra.qctr = h->d_qctr;
+#ifdef AGV_ROLL_PROF
+    if (getenv("AGV_ROLL_PROF")) {
+        if (!h->d_prof) CUDA_TRY(cudaMalloc(&h->d_prof, sizeof(unsigned long long) * 8 * (size_t)d.E));
+        CUDA_TRY(cudaMemsetAsync(h->d_prof, 0, sizeof(unsigned long long) * 8 * (size_t)d.E, st));
+        ra.prof = h->d_prof;
+    }
+#endif
     ra.vec_ok = (d.N % 8 == 0) && (((uintptr_t)obs_dev | (uintptr_t)next_obs_dev) & 15) == 0;
     // per-AGV outputs default to "no turn" (the kernel only writes the turns that happen)
     if (act_out_dev) CUDA_TRY(cudaMemsetAsync(act_out_dev, 0xFF, n, st));
@@ -587,7 +596,7 @@ int agv_destroy(AgvHandle *h) {
     }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
-    cudaFree(h->d_order); cudaFree(h->d_qctr);
+    cudaFree(h->d_order); cudaFree(h->d_qctr); cudaFree(h->d_prof);
     for (int b = 0; b < 2; b++) {
         cudaFree(h->d_scr[b]);
         cudaFree(h->r_action[b]); cudaFree(h->r_act_out[b]); cudaFree(h->r_reward[b]); cudaFree(h->r_done[b]);
@@ -942,7 +951,8 @@ int agv_read_counters(AgvHandle *h, uint64_t out[3], void *stream) {
     CUDA_TRY(cudaMemcpyAsync(tmp, h->d_counters, sizeof(tmp), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemsetAsync(h->d_counters, 0, sizeof(tmp), st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    if (getenv("AGV_PROF_DUMP")) {
+    static const bool dump = getenv("AGV_PROF_DUMP") != nullptr;  // profiling builds only; read once
+    if (dump) {
         fprintf(stderr, "agv prof:");
         for (int i = 3; i < 48; i++) fprintf(stderr, " %llu", tmp[i]);
         fprintf(stderr, "\n");
@@ -974,6 +984,16 @@ int agv_bfs_field(int32_t B, int32_t H, int32_t W, const uint8_t *valid_dev, con
 #define CALL(NW_, RPL_) return launch_warps(k_bfs_field<NW_, RPL_>, B, 0, (cudaStream_t)stream, B, H, W, valid_dev, target_dev, dist_dev)
     DISPATCH(h, CALL);
 #undef CALL
+}
+
+int agv_rollout_profile(AgvHandle *h, uint64_t *out_host, void *stream) {
+    if (!h || !out_host) return AGV_E_INVALID;
+    if (!h->d_prof) return AGV_E_UNSUPPORTED;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaMemcpyAsync(out_host, h->d_prof, sizeof(unsigned long long) * 8 * (size_t)h->cfg.E,
+                             cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    return AGV_OK;
 }
 
 const char *agv_strerror(int status) {

@@ -354,6 +354,10 @@ struct LaneScene {
     bool inflight;  // a request batch is with the worker warps (warp-uniform)
     long long pbfs = 0, pnb = 0;  // profiling builds: cycles / count of BFS sections
     uint32_t cnt_turns, cnt_ended, cnt_bad;
+    // rollout kernel: the task word at the scene's cursor is requested as soon as the cursor moves, so
+    // that the next stage-0 get_task finds it in a register instead of waiting for HBM on the turn chain
+    bool pf = false;
+    uint32_t tk_pf = 0;
 
     __device__ __forceinline__ LaneScene(const DevCfg &cfg, const LaneArgs &args, uint8_t *sm, int lane_, int e0)
         : c(cfg), t(args), lane(lane_), smem(sm), overlap(true), inflight(false), cnt_turns(0), cnt_ended(0), cnt_bad(0) {
@@ -555,11 +559,18 @@ struct LaneScene {
             if ((uint32_t)c.T == n_done) finished = 1;
             return;
         }
-        if (a.stage == 0) a.order = (int)(cursor++);
-        const uint32_t tk = __ldg(tasks_e + a.order);
+        uint32_t tk;
+        if (a.stage == 0) {
+            a.order = (int)(cursor++);
+            if (pf) { tk = tk_pf; tk_pf = __ldg(tasks_e + (cursor < (uint32_t)c.T ? cursor : 0u)); }
+            else tk = __ldg(tasks_e + a.order);
+        } else tk = __ldg(tasks_e + a.order);
         if (a.stage == 1) { a.tx = (tk >> 16) & 255; a.ty = (tk >> 24) & 255; }
         else { a.tx = tk & 255; a.ty = (tk >> 8) & 255; }
         load_condition(a);
+    }
+    __device__ __forceinline__ void prefetch_cursor_task() {
+        if (pf) tk_pf = __ldg(tasks_e + (cursor < (uint32_t)c.T ? cursor : 0u));
     }
     __device__ __forceinline__ void continue_working(Agv &a) {
         a.stage++;
@@ -569,6 +580,7 @@ struct LaneScene {
     // Scene.init (Scene.py:61-65) + create_explorer of AGV 0 (Scene.py:86)
     __device__ __forceinline__ void reset() {
         tick = 0; cursor = 0; n_done = 0; finished = 0; over = 0; acted_mask = 0;
+        prefetch_cursor_task();
         for (int j = 0; j < c.N; j++) { pos_s[j] = (uint16_t)(1 | (1 << 8)); ord_s[j] = 0; meta_s[j] = 0; }
         n_created = 0;
         if (c.N > 0) {

@@ -11,11 +11,11 @@ void note_cuda_error(int e);
 template <int NW, int RPL>
 constexpr int rollout_min_ctas() { return NW * RPL <= 2 ? 4 : (NW * RPL <= 4 ? 2 : 1); }
 
-template <int NW, int RPL, int OBS, int SPW, int NB>
-__global__ void __launch_bounds__(32 * (2 + NB + (OBS == OBS_CLIP ? 1 : 0)), rollout_min_ctas<NW, RPL>())
+template <int NW, int RPL, int OBS, int SPW, int NB, int MODE>
+__global__ void __launch_bounds__(32 * (3 + NB), rollout_min_ctas<NW, RPL>())
 k_rollout(const DevCfg c, const RollArgs ra) {
     extern __shared__ __align__(16) uint8_t lane_smem[];
-    rollout_cta<NW, RPL, OBS, SPW, NB>(c, ra, lane_smem);
+    rollout_cta<NW, RPL, OBS, SPW, NB, MODE>(c, ra, lane_smem);
 }
 
 // Heaviest-first scene order: counting sort of the scenes by the BFS count of their last tick (scene
@@ -65,11 +65,11 @@ static int env_int(const char *name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
-template <int NW, int RPL, int OBS, int SPW, int NB>
+template <int NW, int RPL, int OBS, int SPW, int NB, int MODE>
 static int launch_rollout(const DevCfg &dc, RollArgs ra, unsigned *order, cudaStream_t st) {
     const int smem = plan_rollout<NW, SPW>(dc, ra.la);
-    auto kern = k_rollout<NW, RPL, OBS, SPW, NB>;
-    const int threads = 32 * (2 + NB + (OBS == OBS_CLIP ? 1 : 0));
+    auto kern = k_rollout<NW, RPL, OBS, SPW, NB, MODE>;
+    const int threads = 32 * (3 + NB);  // 2 scene warps, NB BFS workers, the record writer
     if (smem > 227 * 1024) return -4;  // AGV_E_UNSUPPORTED
     static int cps_cached = 0, sms = 0, smem_cached = -1;  // per template instance (one device per process)
     if (smem != smem_cached) {
@@ -102,16 +102,36 @@ static int launch_rollout(const DevCfg &dc, RollArgs ra, unsigned *order, cudaSt
     return 0;
 }
 
+// protocol / policy specialisations (agv_rollout.cuh, MODE): the two modes the rollout exists for get their
+// own kernels; open-loop actions and mixed settings run on the generic one
+#ifndef AGV_ROLL_NB
+#define AGV_ROLL_NB 2   // BFS worker warps per CTA (measured at c3, 16 ticks: 2 -> 1.10e9, 3 -> 1.06e9, 4 -> 0.99e9 AGV-steps/s)
+#endif
+
+template <int NW, int RPL, int OBS>
+static int dispatch_mode(const DevCfg &dc, const RollArgs &ra, unsigned *order, cudaStream_t st) {
+    const LaneArgs &t = ra.la;
+#ifndef AGV_ROLL_GENERIC_ONLY
+    if (t.proto == PROTO_INTELLIGENT && t.policy == POLICY_GUIDED) return launch_rollout<NW, RPL, OBS, 32, AGV_ROLL_NB, 1>(dc, ra, order, st);
+    if (t.proto == PROTO_ASTAR && t.policy == POLICY_ASTAR) return launch_rollout<NW, RPL, OBS, 32, AGV_ROLL_NB, 2>(dc, ra, order, st);
+#endif
+    return launch_rollout<NW, RPL, OBS, 32, AGV_ROLL_NB, 0>(dc, ra, order, st);
+}
+
 template <int NW, int RPL>
 static int dispatch_rollout(const DevCfg &dc, const RollArgs &ra, unsigned *order, cudaStream_t st) {
-    if (ra.la.obs_kind == OBS_CLIP) return launch_rollout<NW, RPL, OBS_CLIP, 32, 3>(dc, ra, order, st);
-    return launch_rollout<NW, RPL, OBS_NONE, 32, 3>(dc, ra, order, st);
+    if (ra.la.obs_kind == OBS_CLIP) return dispatch_mode<NW, RPL, OBS_CLIP>(dc, ra, order, st);
+    return dispatch_mode<NW, RPL, OBS_NONE>(dc, ra, order, st);
 }
 
 // covers no-observation and 3x7x7 limited-visual rollouts without the shaped reward; everything else
 // returns AGV_E_UNSUPPORTED and the caller falls back to n_ticks launches of agv_tick
 int lanes_rollout(const DevCfg &dc, int NW, int RPL, const RollArgs &ra, unsigned *order, cudaStream_t st) {
     if (dc.shaped || !(ra.la.obs_kind == OBS_NONE || (ra.la.obs_kind == OBS_CLIP && dc.K == 7))) return -4;
+#ifdef AGV_ROLL_ONLY12   // tuning builds: only the 64 x 64 shape (compile time)
+    if (NW == 1 && RPL == 2) return dispatch_rollout<1, 2>(dc, ra, order, st);
+    return -4;
+#endif
     if (NW == 1 && RPL == 1) return dispatch_rollout<1, 1>(dc, ra, order, st);
     if (NW == 1 && RPL == 2) return dispatch_rollout<1, 2>(dc, ra, order, st);
     if (NW == 1 && RPL == 4) return dispatch_rollout<1, 4>(dc, ra, order, st);

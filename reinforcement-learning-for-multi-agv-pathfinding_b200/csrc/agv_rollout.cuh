@@ -10,12 +10,14 @@
 // scene from a global queue (heaviest first -- ordered by the BFS count of the scene's last tick)
 // and loads it.  Long scenes start first and short ones fill in behind them.
 //
-// Warp roles in a CTA:  warp 0 / 1       scene warps: the slots whose last tick was light / heavy
-//                                        (a slot migrates between them at tick boundaries)
-//                       warps 2..NB+1    BFS workers: level-synchronous BFS requests + slot swaps
-//                       warp NB+2        record writer (OBS_CLIP): turns the packed 49-bit windows
-//                                        of a finished scene-tick into [3,7,7] bf16 records with
+// Warp roles in a CTA:  warps 0..NB-1    BFS workers: level-synchronous BFS requests + slot swaps
+//                       warp NB          record writer: unpacks the per-turn records of a finished
+//                                        scene-tick -- act / reward / done / plen with coalesced stores,
+//                                        the packed 49-bit windows into [3,7,7] bf16 records with
 //                                        16-byte stores (8 records = 147 uint4, always aligned)
+//                       warps NB+1 / +2  scene warps: the slots whose last tick was heavy / light
+//                                        (a slot migrates between them at tick boundaries); highest
+//                                        warp ids = first pick of the issue arbiter
 // Results are bit-identical to n_ticks calls of agv_tick (tests/test_gpu_rollout.py).
 #pragma once
 #include "agv_async.cuh"
@@ -24,14 +26,47 @@ namespace agv {
 
 constexpr int ROLL_RING = 32;  // tick-end record requests in flight per scene warp
 
+// Poll intervals of the idle warps.  Every poll is ~25 issued instructions on the half-rate ALU pipe the
+// scene warps' turn chains live on: with 400 / 100 ns everywhere (agv_async.cuh) the polls were half of
+// the 5.2e9 instructions of a 16-tick c3 rollout (ncu: smsp__issue_active 50 %, ALU pipe 53 %).  The
+// record writer is never on a scene's critical path; a BFS takes >= 3 us, so 1 us of wake-up is cheap.
+#ifndef AGV_ROLL_WORKER_NS
+#define AGV_ROLL_WORKER_NS 1000
+#endif
+#ifndef AGV_ROLL_WRITER_NS
+#define AGV_ROLL_WRITER_NS 4000
+#endif
+#ifndef AGV_ROLL_IDLE_NS
+#define AGV_ROLL_IDLE_NS 2000   // scene warp without any scene (waiting for a hand-over)
+#endif
+#ifndef AGV_ROLL_WAIT_NS
+#define AGV_ROLL_WAIT_NS 200    // scene warp whose scenes all wait for BFS answers
+#endif
+
 struct RollArgs {
     LaneArgs la;              // proto / policy / obs kind, tick-0 base pointers, shared-memory plan
     int K;                    // ticks per scene
     int vec_ok;               // N % 8 == 0 and 16-byte aligned rings: vector-store path
-    unsigned long long *scr_obs, *scr_next;  // [K*E*N] packed window records (wm | tpos << 49)
+    // per-turn records of the scene lanes, unpacked by the record writer when the scene-tick is over:
+    // scr_turn [K*E*N] {wm | tpos << 49, reward f32 | plen << 32 | action << 48 | done << 56}
+    // (wm = 49-bit window of matrix (b) before the move), scr_next [K*E*N] wm | tpos << 49 after the move
+    ulonglong2 *scr_turn;
+    unsigned long long *scr_next;
     const unsigned *order;    // [E] scene indices, heaviest first
     unsigned *qctr;           // next entry of `order` to hand out
+    unsigned long long *prof; // -DAGV_ROLL_PROF builds: [E][8] per-scene timeline (agv_rollout_profile)
 };
+
+#ifdef AGV_ROLL_PROF
+__device__ __forceinline__ unsigned long long roll_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define RPROF(...) __VA_ARGS__
+#else
+#define RPROF(...)
+#endif
 
 struct RollShared {
     unsigned bfs_state[32];   // per slot: 0 idle, 1 BFS posted, 2 taken, 3 answered, 4 swap posted, 5 swap taken
@@ -50,7 +85,96 @@ struct RollShared {
     unsigned long long recbits[64][3];     // writer staging: the 147-bit strings of one scene-tick's records
 };
 
-constexpr int LS_IDLE = 4, LS_NEWTICK = 5;
+constexpr int LS_IDLE = 4, LS_NEWTICK = 5, LS_TICKEND = 6;
+#ifndef AGV_ROLL_SLOW_EVERY
+#define AGV_ROLL_SLOW_EVERY 4   // power of two: the light scene warp runs its slow section every n-th iteration
+#endif
+
+// lane_monotone (agv_lanes.cuh) reshaped for the latency of ONE warp (nothing else runs on the scene warp's
+// SM sub-partition, so every instruction and every exposed load latency of the row loop is on the scene's
+// turn chain; the plain loop measured ~100 cycles per row, 6 k of the 14 k cycles of a warp iteration):
+//  * the loop covers only the rows strictly between the target's and the start's; a lane that is through
+//    re-reads its last row, which is idempotent (fill(fill(x)) == fill(x)), so no per-row snapshot selects;
+//    the start row is applied once after the loop (its loads are issued before the loop);
+//  * the row loads of the next pair of rows are issued while the current pair runs through the fill chain.
+// 13 instead of 23 instructions per row.  Same result as lane_monotone for every input.
+template <int NW>
+__device__ __forceinline__ int lane_monotone_pf(bool need, const uint64_t *tab, int HN, const uint64_t *occ,
+                                                const uint64_t *occm, int loaded, int sx, int sy, int tx, int ty,
+                                                int &len) {
+    constexpr int WB = 64 * NW;
+    const int dxs = (tx > sx) - (tx < sx), dys = (ty > sy) - (ty < sy);
+    const bool mirror = tx > sx;
+    const int sxm = mirror ? WB - 1 - sx : sx, txm = mirror ? WB - 1 - tx : tx;  // txm <= sxm
+    const bool flip = mirror && !mirror_copy<NW>();
+    const uint64_t *bp = tab + ((mirror && mirror_copy<NW>() ? 2 : 0) + loaded) * HN + ty * NW;
+    const uint64_t *op = (mirror && mirror_copy<NW>() ? occm : occ) + ty * NW;
+    const int step = -dys * NW;
+    const Row<NW> box = rrange<NW>(txm, sxm);
+    Row<NW> reach = rbit<NW>(txm);
+    const int n = need ? abs(ty - sy) : 0;  // rows after the target's; row n is the start's
+    const int nm = max(n - 1, 0);           // rows strictly between
+    if (!need) { bp = tab; op = tab; }
+    Row<NW> b0 = ldrow<NW>(bp), o0 = ldrow<NW>(op);
+    Row<NW> bs = ldrow<NW>(bp + n * step), os = ldrow<NW>(op + n * step);  // the start's row
+    Row<NW> nb[2], no[2];
+#pragma unroll
+    for (int q = 0; q < 2; q++) { const int k = min(1 + q, nm) * step; nb[q] = ldrow<NW>(bp + k); no[q] = ldrow<NW>(op + k); }
+    {   // the target's row: the target cell itself is valid unless occupied
+        if (!mirror_copy<NW>() && flip) { b0 = rmirror(b0); o0 = rmirror(o0); }
+        b0 = ror(b0, reach);
+#pragma unroll
+        for (int i = 0; i < NW; i++) b0.w[i] = b0.w[i] & ~o0.w[i] & box.w[i];
+        reach = rfill_up(rand_(reach, b0), b0);
+    }
+    const Row<NW> r0 = reach;
+    const int nmax = __reduce_max_sync(FULL, nm);
+#pragma unroll 1
+    for (int it = 1; it <= nmax; it += 2) {
+        Row<NW> cb[2], co[2];
+#pragma unroll
+        for (int q = 0; q < 2; q++) { cb[q] = nb[q]; co[q] = no[q]; }
+#pragma unroll
+        for (int q = 0; q < 2; q++) { const int k = min(it + 2 + q, nm) * step; nb[q] = ldrow<NW>(bp + k); no[q] = ldrow<NW>(op + k); }
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            Row<NW> b = cb[q], o = co[q];
+            if (!mirror_copy<NW>() && flip) { b = rmirror(b); o = rmirror(o); }
+#pragma unroll
+            for (int i = 0; i < NW; i++) b.w[i] = b.w[i] & ~o.w[i] & box.w[i];
+            reach = rfill_up(rand_(reach, b), b);
+        }
+    }
+    if (nm == 0) reach = r0;  // (the loop re-read the target's row without its target bit: discard)
+    // reach = row before the start's (n >= 1) or the target's own row (n == 0)
+    Row<NW> rfin = reach, pfin = rzero<NW>();
+    if (n >= 1) {
+        pfin = reach;
+        if (!mirror_copy<NW>() && flip) { bs = rmirror(bs); os = rmirror(os); }
+#pragma unroll
+        for (int i = 0; i < NW; i++) bs.w[i] = bs.w[i] & ~os.w[i] & box.w[i];
+        rfin = rfill_up(rand_(reach, bs), bs);
+    }
+    len = 0;
+    int act = -1;
+    if (need) {
+        // the start's own row may be empty (the start cell is occupied by the AGV itself, hence
+        // invalid) while the vertical neighbour in the row before it is still on a path
+        const bool okH = dxs != 0 && rtest(rfin, sxm - 1);
+        const bool okV = dys != 0 && rtest(pfin, sxm);
+        if (okH && dxs > 0) act = A_RIGHT;
+        else if (okV && dys > 0) act = A_DOWN;
+        else if (okV && dys < 0) act = A_UP;
+        else if (okH && dxs < 0) act = A_LEFT;
+        if (act >= 0) len = abs(tx - sx) + abs(ty - sy);
+    }
+    return act;
+}
+
+// (A bidirectional variant -- target-side chain and two start-side chains on the mirrored copies, meeting
+// in the middle row: half the dependent depth, 3 independent chains -- was parity-green but slower, 6.8 k
+// vs 4.9 k cycles per warp iteration: 45 instead of 17 instructions per row step, and the warp was not
+// dependency-bound but losing the issue arbitration, see rollout_cta.)
 
 // ------------------------------------------------------------------ slot <-> HBM (one warp, coalesced)
 template <int NW>
@@ -121,7 +245,7 @@ __device__ __forceinline__ void roll_worker(const DevCfg &c, const RollArgs &ra,
         unsigned m = __ballot_sync(FULL, s == 1u || s == 4u);
         if (!m) {
             if (*vexit) return;
-            __nanosleep(AGV_POLL_NS);
+            __nanosleep(AGV_ROLL_WORKER_NS);
             continue;
         }
         int j = -1;
@@ -174,15 +298,16 @@ __device__ __forceinline__ void roll_worker(const DevCfg &c, const RollArgs &ra,
 // are 1176 bits = 147 x 8 bits, and 8 bits expand to one uint4 of bf16 -- so with N % 8 == 0 every
 // store is a full, aligned 16-byte vector.  Records of AGVs without a turn inside a written group
 // are zero-filled (the consumer masks with act_out >= 0, as for agv_tick).
-__device__ __forceinline__ void roll_expand(const RollArgs &ra, RollShared *sh, uint16_t *dst,
-                                            const unsigned long long *scr, unsigned rec_base, uint64_t acted, int lane) {
+// (scr: packed windows, `stride` 64-bit words apart)
+static __device__ __noinline__ void roll_expand(int vec_ok, RollShared *sh, uint16_t *dst, const unsigned long long *scr,
+                                         int stride, unsigned rec_base, uint64_t acted, int lane) {
     if (!acted) return;
     const int n_hi = 64 - __clzll((long long)acted);
     const int G = (n_hi + 7) >> 3;
-    if (!ra.vec_ok) {
+    if (!vec_ok) {
         for (int r = 0; r < n_hi; r++) {
             if (!((acted >> r) & 1ull)) continue;
-            const unsigned long long m = __ldcg(scr + rec_base + r);
+            const unsigned long long m = __ldcg(scr + ((size_t)rec_base + r) * stride);
             expand_clip7(dst + ((size_t)rec_base + r) * 147, m & ((1ull << 49) - 1ull), (int)((m >> 49) & 63ull), lane);
         }
         return;
@@ -192,7 +317,7 @@ __device__ __forceinline__ void roll_expand(const RollArgs &ra, RollShared *sh, 
         const int r = lane + 32 * q;
         if (r < 8 * G) {
             const bool valid = (acted >> r) & 1ull;
-            const unsigned long long m = valid ? __ldcg(scr + rec_base + r) : 0ull;
+            const unsigned long long m = valid ? __ldcg(scr + ((size_t)rec_base + r) * stride) : 0ull;
             const unsigned long long wm = m & ((1ull << 49) - 1ull);
             const int tp = (int)((m >> 49) & 63ull);
             unsigned long long w0 = 0ull, w1 = 0ull, w2 = 0ull;
@@ -206,7 +331,9 @@ __device__ __forceinline__ void roll_expand(const RollArgs &ra, RollShared *sh, 
     }
     __syncwarp();
     uint4 *d4 = reinterpret_cast<uint4 *>(dst + (size_t)rec_base * 147);
-    const int nv = G * 147;
+    // up to the end of the last record with a turn; the last vector may reach into the first <= 7 elements of
+    // the record after it, which are zero in every record (its first-channel cells 0..6; the centre is 24)
+    const int nv = (147 * n_hi + 7) >> 3;
     for (int v = lane; v < nv; v += 32) {
         const unsigned bit = 8u * (unsigned)v;
         const unsigned r = bit / 147u, off = bit - r * 147u;
@@ -224,6 +351,26 @@ __device__ __forceinline__ void roll_expand(const RollArgs &ra, RollShared *sh, 
         d4[v] = o;
     }
     __syncwarp();
+}
+
+// act / done / reward / plen of a finished scene-tick: the scene lane left them packed in the second word
+// of its per-turn records (one 16-byte store per turn instead of five scattered ones on the turn chain);
+// here they go out to the [n_ticks, E, N] rings, one coalesced store per array
+__device__ __forceinline__ void roll_unpack(const RollArgs &ra, unsigned rec_base, uint64_t acted, int lane) {
+    const LaneArgs &t = ra.la;
+    const unsigned long long *scr = reinterpret_cast<const unsigned long long *>(ra.scr_turn);
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        const int r = lane + 32 * q;
+        if ((acted >> r) & 1ull) {
+            const size_t rec = (size_t)rec_base + r;
+            const unsigned long long hi = __ldcg(scr + rec * 2 + 1);
+            if (t.reward) t.reward[rec] = __uint_as_float((unsigned)hi);
+            if (t.plen) t.plen[rec] = (uint16_t)(hi >> 32);
+            if (t.act_out) t.act_out[rec] = (int8_t)(hi >> 48);
+            if (t.done) t.done[rec] = (uint8_t)(hi >> 56);
+        }
+    }
 }
 
 __device__ __forceinline__ void roll_writer(const RollArgs &ra, uint8_t *smem) {
@@ -244,8 +391,9 @@ __device__ __forceinline__ void roll_writer(const RollArgs &ra, uint8_t *smem) {
             for (; mine[q] != h; mine[q]++) {
                 const uint4 rq = sh->enc_ring[q][mine[q] % ROLL_RING];
                 const uint64_t acted = (uint64_t)rq.y | ((uint64_t)rq.z << 32);
-                if (t.obs) roll_expand(ra, sh, t.obs, ra.scr_obs, rq.x, acted, lane);
-                if (t.next_obs) roll_expand(ra, sh, t.next_obs, ra.scr_next, rq.x, acted, lane);
+                roll_unpack(ra, rq.x, acted, lane);
+                if (t.obs) roll_expand(ra.vec_ok, sh, t.obs, reinterpret_cast<const unsigned long long *>(ra.scr_turn), 2, rq.x, acted, lane);
+                if (t.next_obs) roll_expand(ra.vec_ok, sh, t.next_obs, ra.scr_next, 1, rq.x, acted, lane);
             }
             __threadfence_block();
             __syncwarp();
@@ -256,12 +404,23 @@ __device__ __forceinline__ void roll_writer(const RollArgs &ra, uint8_t *smem) {
             if (vhead[0] == mine[0] && vhead[1] == mine[1]) return;
             continue;
         }
-        __nanosleep(AGV_POLL_NS);
+        __nanosleep(AGV_ROLL_WRITER_NS);
     }
 }
 
 // ------------------------------------------------------------------ scene warp
-template <int NW, int RPL, int OBS, int SPW>
+// MODE fixes protocol and policy at compile time: 1 = "intelligent" + A* guidance (AG-DQN's guided branch,
+// the headline), 2 = A_star control mode (Expert rollouts), 0 = whatever the call says (open-loop actions).
+// The specialised kernels carry a third less code: a scene-warp iteration streams its whole body through
+// the 6 KB L0 / 32 KB L1.5 instruction caches once per turn, and instruction fetch was the top stall of the
+// generic body (ncu source view: stall_no_inst 37 % of the samples outside the row-DP loop).
+//
+// One loop iteration = a FAST section (finish the turns that have their action, start the next ones: window,
+// row DP, BFS request) and, every 4th iteration only, a SLOW section (hand-overs, tick boundaries, spawn,
+// record requests, BFS answers, exit test).  The 32 scenes of a warp are at different points of their ticks,
+// so tick-boundary code would otherwise run -- for one or two lanes -- in nearly every iteration.  The heavy
+// warp (few scenes, all waiting for BFS answers most of the time) runs the slow section every iteration.
+template <int NW, int RPL, int OBS, int SPW, int MODE>
 __device__ __forceinline__ void roll_scene_warp(const DevCfg &c, const RollArgs &ra, uint8_t *smem, const int which) {
     const LaneArgs &t = ra.la;
     const int lane = threadIdx.x & 31;
@@ -271,91 +430,137 @@ __device__ __forceinline__ void roll_scene_warp(const DevCfg &c, const RollArgs 
     volatile unsigned *vdone_slots = &sh->done_slots;
     volatile unsigned *vhead = &sh->enc_head[which], *vtail = &sh->enc_tail[which];
     const int N = c.N, K = ra.K;
+    const int proto = MODE == 1 ? PROTO_INTELLIGENT : (MODE == 2 ? PROTO_ASTAR : t.proto);
+    const int policy = MODE == 1 ? POLICY_GUIDED : (MODE == 2 ? POLICY_ASTAR : t.policy);
     const uint64_t om_a = N > 1 ? ~0ull : 0ull;
     const bool want_obs = OBS == OBS_CLIP && t.obs != nullptr, want_next = OBS == OBS_CLIP && t.next_obs != nullptr;
     const uint64_t *zr = reinterpret_cast<const uint64_t *>(smem + t.off_zero);
-    ws.has = false; ws.e = 0; ws.tasks_e = c.tasks;
+    ws.has = false; ws.e = 0; ws.tasks_e = c.tasks; ws.pf = true;
     ws.over = 1; ws.finished = 0; ws.n_created = 0; ws.tick = 0; ws.cursor = 0; ws.n_done = 0; ws.acted_mask = 0;
 
     int st = LS_IDLE, i = 0, n_loop = 0, k = 0;
     unsigned n_bfs = 0;     // BFS searches of the tick in progress (weight of the scene once the tick is over)
     unsigned rec0 = 0;      // (k * E + e) * N: first output record of the scene's tick in progress
-    unsigned head = 0;
+    unsigned head = 0, it = 0;
     Agv a;
     a.x = a.y = a.tx = a.ty = 1; a.stage = a.loaded = a.idle = a.order = 0;
     int action = -1, plen = 0, given = -1;
     int pf_idx = -1, pf_val = -1;
     bool guard = false;
+    unsigned long long wm_turn = 0ull;  // packed window of the turn in progress (obs before the move)
+    RPROF(long long t_post = 0; long long q_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long qc_ = clock64(); long long iters_ = 0; long long rows_ = 0;)
+#ifdef AGV_ROLL_PROF
+#define RQ(k) { const long long n_ = clock64(); q_[k] += n_ - qc_; qc_ = n_; }
+#else
+#define RQ(k)
+#endif
 
     for (;;) {
-        if (*vdone_slots >= (unsigned)SPW) break;  // every slot of the CTA has found the queue empty
-        const bool pick = st == LS_IDLE && vctl[lane] == 2u + (unsigned)which;
-        if (!__any_sync(FULL, pick || st == LS_NEWTICK || st == LS_START || st == LS_HAVE ||
-                                  (st == LS_WAIT && vs[lane] == 3u))) {
-            __nanosleep(100);
-            continue;
-        }
-        // ---- 0: slots handed to this warp (freshly loaded by a worker, or migrated from the other scene warp)
-        if (pick) {
-            __threadfence_block();
-            ws.hdr_to_regs();
-            ws.e = *reinterpret_cast<volatile int *>(&sh->slot_e[lane]);
-            ws.tasks_e = c.tasks + (size_t)ws.e * c.T;
-            k = *reinterpret_cast<volatile int *>(&sh->slot_k[lane]);
-            ws.overlap = (*reinterpret_cast<volatile unsigned *>(&sh->slot_fl[lane]) & 1u) != 0u;
-            n_bfs = ws.hdr_w[6];
-            vctl[lane] = (unsigned)which;
-            st = LS_NEWTICK;
-        }
-        // ---- 1: tick boundary
-        if (st == LS_NEWTICK) {
-            const int w_new = n_bfs >= (unsigned)AGV_HEAVY_BFS ? 1 : 0;
-            if (k >= K) {          // this scene is through: a worker stores it and fetches the next one
-                ws.regs_to_hdr(); ws.hdr_w[6] = n_bfs;
+        const bool any_run = __any_sync(FULL, st == LS_START || st == LS_HAVE);
+        if (which == 1 || (it & (unsigned)(AGV_ROLL_SLOW_EVERY - 1)) == 0u || !any_run) {
+            // ================================================================ slow section
+            if (*vdone_slots >= (unsigned)SPW) break;  // every slot of the CTA has found the queue empty
+            const bool pick = st == LS_IDLE && vctl[lane] == 2u + (unsigned)which;
+            const bool ans = st == LS_WAIT && vs[lane] == 3u;
+            if (!any_run && !__any_sync(FULL, pick || ans || st == LS_NEWTICK || st == LS_TICKEND)) {
+                if (__any_sync(FULL, st == LS_WAIT)) __nanosleep(AGV_ROLL_WAIT_NS);
+                else __nanosleep(AGV_ROLL_IDLE_NS);
+                RQ(0)
+                continue;
+            }
+            // ---- slots handed to this warp (freshly loaded by a worker, or migrated from the other scene warp)
+            if (pick) {
                 __threadfence_block();
-                vs[lane] = 4u;
-                st = LS_IDLE;
-            } else if (w_new != which) {  // its last tick was heavy (light): continue on the other scene warp
-                ws.regs_to_hdr(); ws.hdr_w[6] = n_bfs;
-                sh->slot_k[lane] = k; sh->slot_fl[lane] = ws.overlap ? 1u : 0u;
-                __threadfence_block();
-                vctl[lane] = 2u + (unsigned)w_new;
-                st = LS_IDLE;
-            } else {
-                bool live = true;
-                if (ws.over) {
-                    if (c.auto_reset) {  // Scene.init: every AGV back at (1,1), AGV 0 created
-                        ws.reset();
-                        for (int q = 0; q < ws.HN; q++) { ws.occ[q] = 0ull; if (mirror_copy<NW>()) ws.occm[q] = 0ull; }
-                        ws.occ_set(0, 0);
-                        ws.overlap = false;
-                    } else live = false;
-                }
-                if (!live) k = K;  // a finished episode without auto-reset: the remaining ticks do nothing
-                else {
-                    ws.tick++; ws.acted_mask = 0;
-                    i = 0; n_loop = min(N, ws.n_created); n_bfs = 0; pf_idx = -1;
-                    rec0 = ((unsigned)k * (unsigned)c.E + (unsigned)ws.e) * (unsigned)N;
-                    st = LS_START;
+                ws.hdr_to_regs();
+                ws.e = *reinterpret_cast<volatile int *>(&sh->slot_e[lane]);
+                ws.tasks_e = c.tasks + (size_t)ws.e * c.T;
+                ws.prefetch_cursor_task();
+                k = *reinterpret_cast<volatile int *>(&sh->slot_k[lane]);
+                ws.overlap = (*reinterpret_cast<volatile unsigned *>(&sh->slot_fl[lane]) & 1u) != 0u;
+                n_bfs = ws.hdr_w[6];
+                vctl[lane] = (unsigned)which;
+                st = LS_NEWTICK;
+                RPROF(if (ra.prof) { if (k == 0) ra.prof[(size_t)ws.e * 8 + 4] = roll_now(); atomicAdd(ra.prof + (size_t)ws.e * 8 + 5, 1ull); })
+            }
+            // ---- end of a tick: Scene.check_new_veh (Scene.py:164), then the finished scene-tick goes to the
+            // record writer: {first record, who took a turn}
+            const bool tick_end = st == LS_TICKEND;
+            if (tick_end) {
+                if (!ws.over) ws.spawn();
+                k++;
+                st = LS_NEWTICK;
+                RPROF(if (ra.prof) { atomicAdd(ra.prof + (size_t)ws.e * 8 + 1, (unsigned long long)n_bfs); atomicAdd(ra.prof + (size_t)ws.e * 8 + 2, (unsigned long long)__popcll(ws.acted_mask)); })
+            }
+            {
+                const bool post = tick_end && ws.acted_mask != 0ull;
+                const unsigned pend = __ballot_sync(FULL, post);
+                if (pend) {
+                    const int n = __popc(pend);
+                    while ((int)(head + (unsigned)n - *vtail) > ROLL_RING) __nanosleep(40);
+                    if (post)
+                        sh->enc_ring[which][(head + (unsigned)__popc(pend & ((1u << lane) - 1u))) % ROLL_RING] =
+                            make_uint4(rec0, (unsigned)ws.acted_mask, (unsigned)(ws.acted_mask >> 32), 0u);
+                    __threadfence_block();  // also orders the lane's per-turn records before the request
+                    __syncwarp();
+                    head += (unsigned)n;
+                    if (lane == 0) *vhead = head;
                 }
             }
+            // ---- start of a tick
+            if (st == LS_NEWTICK) {
+                const int w_new = n_bfs >= (unsigned)AGV_HEAVY_BFS ? 1 : 0;
+                if (k >= K) {          // this scene is through: a worker stores it and fetches the next one
+                    ws.regs_to_hdr(); ws.hdr_w[6] = n_bfs;
+                    __threadfence_block();
+                    vs[lane] = 4u;
+                    st = LS_IDLE;
+                    RPROF(if (ra.prof) { ra.prof[(size_t)ws.e * 8 + 0] = roll_now(); ra.prof[(size_t)ws.e * 8 + 6] = blockIdx.x; })
+                } else if (w_new != which) {  // its last tick was heavy (light): continue on the other scene warp
+                    ws.regs_to_hdr(); ws.hdr_w[6] = n_bfs;
+                    sh->slot_k[lane] = k; sh->slot_fl[lane] = ws.overlap ? 1u : 0u;
+                    __threadfence_block();
+                    vctl[lane] = 2u + (unsigned)w_new;
+                    st = LS_IDLE;
+                } else {
+                    bool live = true;
+                    if (ws.over) {
+                        if (c.auto_reset) {  // Scene.init: every AGV back at (1,1), AGV 0 created
+                            ws.reset();
+                            for (int q = 0; q < ws.HN; q++) { ws.occ[q] = 0ull; if (mirror_copy<NW>()) ws.occm[q] = 0ull; }
+                            ws.occ_set(0, 0);
+                            ws.overlap = false;
+                        } else live = false;
+                    }
+                    if (!live) k = K;  // a finished episode without auto-reset: the remaining ticks do nothing
+                    else {
+                        ws.tick++; ws.acted_mask = 0;
+                        i = 0; n_loop = min(N, ws.n_created); n_bfs = 0; pf_idx = -1;
+                        rec0 = ((unsigned)k * (unsigned)c.E + (unsigned)ws.e) * (unsigned)N;
+                        st = LS_START;
+                    }
+                }
+            }
+            // ---- answers of the BFS workers
+            if (ans) {
+                __threadfence_block();
+                const unsigned r = *reinterpret_cast<volatile unsigned *>(&sh->bfs_res[lane]);
+                vs[lane] = 0u;
+                action = (int)(r & 0xFFu); plen = (int)(r >> 8);
+                if (MODE != 1 && guard) { ws.occ_clear(0, 0); guard = false; }
+                st = LS_HAVE;
+                RPROF(if (ra.prof) { atomicAdd(ra.prof + (size_t)ws.e * 8 + 3, (unsigned long long)(clock64() - t_post)); atomicAdd(ra.prof + (size_t)ws.e * 8 + 7, (unsigned long long)plen); })
+            }
+            RQ(1)
         }
-        // ---- A: answers of the BFS workers
-        if (st == LS_WAIT && vs[lane] == 3u) {
-            __threadfence_block();
-            const unsigned r = *reinterpret_cast<volatile unsigned *>(&sh->bfs_res[lane]);
-            vs[lane] = 0u;
-            action = (int)(r & 0xFFu); plen = (int)(r >> 8);
-            if (guard) { ws.occ_clear(0, 0); guard = false; }
-            st = LS_HAVE;
-        }
+        it++;
+        RPROF(iters_++;)
+        // ==================================================================== fast section
         // ---- B: finish the turn of the lanes that have their action
         // (Explorer.check_action, Explorer.py:151-208; Scene.py:155-158)
-        const bool fin = st == LS_HAVE;
-        if (fin) {
-            const bool guided = (t.policy == POLICY_GUIDED) || (t.policy == POLICY_GIVEN && given < 0);
-            const bool pol_a = !guided && t.policy == POLICY_ASTAR;
-            if (!guided && !pol_a && action > A_STOP) { ws.cnt_bad++; action = A_STOP; }
+        if (st == LS_HAVE) {
+            const bool guided = (policy == POLICY_GUIDED) || (policy == POLICY_GIVEN && given < 0);
+            const bool pol_a = !guided && policy == POLICY_ASTAR;
+            if (MODE == 0 && !guided && !pol_a && action > A_STOP) { ws.cnt_bad++; action = A_STOP; }
             const int dx = (action == A_RIGHT) - (action == A_LEFT);
             const int dy = (action == A_DOWN) - (action == A_UP);
             const int nx = a.x + dx, ny = a.y + dy;
@@ -367,18 +572,18 @@ __device__ __forceinline__ void roll_scene_warp(const DevCfg &c, const RollArgs 
                 const bool at_target = (nx == a.tx) && (ny == a.ty);
                 if (code == 1 && a.loaded && !at_target) { r = -1; end = 1; }
                 else if (code == 2 && !at_target) { r = -1; end = 1; }
-                else if (t.proto == PROTO_INTELLIGENT && ws.other_at_from(i, nx | (ny << 8), a.x | (a.y << 8))) { r = -1; end = 1; }
+                else if (proto == PROTO_INTELLIGENT && ws.other_at_from(i, nx | (ny << 8), a.x | (a.y << 8))) { r = -1; end = 1; }
                 else if (at_target) { r = 1; ws.continue_working(a); }
             }
             // Explorer.py:145-148: the move is applied iff not is_end
-            if (t.proto != PROTO_INTELLIGENT && !guided && !pol_a) ws.overlap = true;
+            if (MODE == 0 && proto != PROTO_INTELLIGENT && !guided && !pol_a) ws.overlap = true;
             if (!end && (dx | dy)) {
                 const bool still = ws.other_at_from(i, a.x | (a.y << 8), a.x | (a.y << 8));
                 ws.occ_move(a.x - 1, a.y - 1, nx - 1, ny - 1, !still);
                 a.x = nx; a.y = ny;
             }
             ws.store_agv(i, a);
-            if (t.proto == PROTO_INTELLIGENT) {
+            if (proto == PROTO_INTELLIGENT) {
                 if (ws.finished || (long long)ws.tick >= c.max_steps) end = 1;  // Scene.py:155
                 if (end) ws.over = 1;
             } else {
@@ -388,10 +593,11 @@ __device__ __forceinline__ void roll_scene_warp(const DevCfg &c, const RollArgs 
             ws.cnt_turns++;
             ws.cnt_ended += end;
             const size_t rec = (size_t)rec0 + i;
-            if (t.act_out) t.act_out[rec] = (int8_t)action;
-            if (t.done) t.done[rec] = (uint8_t)end;
-            if (t.reward) t.reward[rec] = (float)r;
-            if (t.plen) t.plen[rec] = (uint16_t)plen;
+            // one 16-byte record per turn: {window before the move, reward | plen | action | done}
+            ra.scr_turn[rec] = make_ulonglong2(wm_turn, (unsigned long long)__float_as_uint((float)r) |
+                                                            ((unsigned long long)(plen & 0xFFFF) << 32) |
+                                                            ((unsigned long long)(action & 0xFF) << 48) |
+                                                            ((unsigned long long)end << 56));
             if (want_next) {  // store_info's create_state on the snapshot after the move (Scene.py:156)
                 bool shared = false;
                 if (ws.overlap) shared = ws.other_at(i, a.x | (a.y << 8));
@@ -403,43 +609,24 @@ __device__ __forceinline__ void roll_scene_warp(const DevCfg &c, const RollArgs 
             i++;
             st = LS_START;
         }
-        // ---- C: start the next turn (Scene.py:124-134 skip rules first) -- or end the tick
-        bool tick_end = false;
+        RQ(2)
+        // ---- C: start the next turn (Scene.py:124-134 skip rules first) -- or leave the tick's end to the
+        // slow section
         if (st == LS_START) {
             for (;;) {
-                if (i >= n_loop || ws.over) { tick_end = true; break; }
-                if (ws.finished) { ws.over = 1; ws.cnt_ended++; tick_end = true; break; }  // Scene.py:129-130
-                if (!((ws.meta_s[i] >> 3) & 1)) break;                                      // idle AGVs are skipped
+                if (i >= n_loop || ws.over) { st = LS_TICKEND; break; }
+                if (ws.finished) { ws.over = 1; ws.cnt_ended++; st = LS_TICKEND; break; }  // Scene.py:129-130
+                if (!((ws.meta_s[i] >> 3) & 1)) break;                                    // idle AGVs are skipped
                 i++;
             }
         }
-        if (tick_end) {
-            if (!ws.over) ws.spawn();  // Scene.check_new_veh, Scene.py:164
-            k++;
-            st = LS_NEWTICK;
-        }
-        if (want_obs || want_next) {
-            // the finished scene-ticks go to the record writer: {first record, who took a turn}
-            const bool post = tick_end && ws.acted_mask != 0ull;
-            const unsigned pend = __ballot_sync(FULL, post);
-            if (pend) {
-                const int n = __popc(pend);
-                while ((int)(head + (unsigned)n - *vtail) > ROLL_RING) __nanosleep(40);
-                if (post)
-                    sh->enc_ring[which][(head + (unsigned)__popc(pend & ((1u << lane) - 1u))) % ROLL_RING] =
-                        make_uint4(rec0, (unsigned)ws.acted_mask, (unsigned)(ws.acted_mask >> 32), 0u);
-                __threadfence_block();  // also orders the lane's packed-window stores before the request
-                __syncwarp();
-                head += (unsigned)n;
-                if (lane == 0) *vhead = head;
-            }
-        }
+        RQ(3)
         const bool act = st == LS_START;
         uint64_t wm_obs = ~0ull;
         if (act) {
             a = ws.load_agv(i);
             given = -1;
-            if (t.policy == POLICY_GIVEN && t.action) {
+            if (MODE == 0 && policy == POLICY_GIVEN && t.action) {
                 // the action of the next AGV index was requested a turn ago (a global load here would
                 // put ~500 cycles of latency on every turn of the scene's chain)
                 given = (pf_idx == i) ? pf_val : (int)t.action[(size_t)rec0 + i];
@@ -452,14 +639,15 @@ __device__ __forceinline__ void roll_scene_warp(const DevCfg &c, const RollArgs 
                 wm_obs = lane_window7<NW>(ws.tab + a.loaded * ws.HN, ws.occ, c.H, a.x - 1, a.y - 1, a.tx - 1, a.ty - 1,
                                           shared);
                 const int tpos = (max(-3, min(3, a.ty - a.y)) + 3) * 7 + max(-3, min(3, a.tx - a.x)) + 3;
-                ra.scr_obs[(size_t)rec0 + i] = wm_obs | ((unsigned long long)tpos << 49);
+                wm_turn = wm_obs | ((unsigned long long)tpos << 49);
             }
         }
+        RQ(5)
         if (__any_sync(FULL, act)) {
-            const bool guided = (t.policy == POLICY_GUIDED) || (t.policy == POLICY_GIVEN && given < 0);
-            const bool pol_a = !guided && t.policy == POLICY_ASTAR;
+            const bool guided = (policy == POLICY_GUIDED) || (policy == POLICY_GIVEN && given < 0);
+            const bool pol_a = !guided && policy == POLICY_ASTAR;
             bool need = act && (guided || pol_a);
-            if (act && !need) { action = given; plen = 0; st = LS_HAVE; }
+            if (MODE == 0 && act && !need) { action = given; plen = 0; st = LS_HAVE; }
             const int sx = a.x - 1, sy = a.y - 1, tx = a.tx - 1, ty = a.ty - 1;
             if (need && sx == tx && sy == ty) { action = A_STOP; plen = 0; st = LS_HAVE; need = false; }
             // boxed in: none of the four neighbour cells is valid in matrix (b) -- they are cells 17, 23,
@@ -469,15 +657,20 @@ __device__ __forceinline__ void roll_scene_warp(const DevCfg &c, const RollArgs 
                 action = A_STOP; plen = 0; st = LS_HAVE; need = false;
             }
             // matrix (a) also blocks (1,1) while uncreated AGVs park there (Explorer.py:274-283)
-            if (need && pol_a && N > 1 && ws.n_created < N && !ws.occ_test(0, 0)) { ws.occ_set(0, 0); guard = true; }
+            if (MODE != 1 && need && pol_a && N > 1 && ws.n_created < N && !ws.occ_test(0, 0)) { ws.occ_set(0, 0); guard = true; }
             const uint64_t om = guided ? ~0ull : om_a;
             int l = 0;
-            const int ma = lane_monotone<NW>(need, ws.tab, ws.HN, om ? ws.occ : zr, om ? ws.occm : zr, a.loaded, sx, sy, tx,
-                                             ty, l);
+            RPROF(rows_ += __reduce_max_sync(FULL, need ? abs(ty - sy) : 0);)
+            RQ(6)
+            const int ma = lane_monotone_pf<NW>(need, ws.tab, ws.HN, om ? ws.occ : zr, om ? ws.occm : zr, a.loaded, sx, sy,
+                                                tx, ty, l);
+            RQ(7)
             if (need) {
                 if (ma >= 0) {
                     action = ma; plen = l; st = LS_HAVE;
-                    if (guard) { ws.occ_clear(0, 0); guard = false; }
+                    if (MODE != 1 && guard) { ws.occ_clear(0, 0); guard = false; }
+                    // about to reach the target: the task word of the next stage will be needed on the chain
+                    if (l <= 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(ws.tasks_e + a.order));
                 } else {  // level-synchronous BFS by a worker warp; this scene waits, the others go on
                     *reinterpret_cast<volatile unsigned *>(&sh->bfs_req[lane]) =
                         (unsigned)sx | ((unsigned)sy << 7) | ((unsigned)tx << 14) | ((unsigned)ty << 21) |
@@ -486,10 +679,20 @@ __device__ __forceinline__ void roll_scene_warp(const DevCfg &c, const RollArgs 
                     vs[lane] = 1u;
                     st = LS_WAIT;
                     n_bfs++;
+                    RPROF(t_post = clock64();)
                 }
             }
         }
+        RQ(6)
     }
+#ifdef AGV_ROLL_PROF
+    if (lane == 0) {  // counters[8 + 10 * which + k]: cycles of phase k, [.. + 8]: iterations, [.. + 9]: warps
+        for (int k_ = 0; k_ < 8; k_++) atomicAdd(c.counters + 8 + 10 * which + k_, (unsigned long long)q_[k_]);
+        atomicAdd(c.counters + 8 + 10 * which + 8, (unsigned long long)iters_);
+        atomicAdd(c.counters + 8 + 10 * which + 9, 1ull);
+        atomicAdd(c.counters + 28 + which, (unsigned long long)rows_);
+    }
+#endif
     __threadfence_block();
     __syncwarp();
     if (lane == 0 && atomicAdd(&sh->done_warps, 1u) == 1u) *reinterpret_cast<volatile int *>(&sh->exit_flag) = 1;
@@ -505,7 +708,7 @@ __device__ __forceinline__ void roll_scene_warp(const DevCfg &c, const RollArgs 
 }
 
 // kernel body: role by warp index
-template <int NW, int RPL, int OBS, int SPW, int NB>
+template <int NW, int RPL, int OBS, int SPW, int NB, int MODE>
 __device__ __forceinline__ void rollout_cta(const DevCfg &c, const RollArgs &ra, uint8_t *smem) {
     const LaneArgs &t = ra.la;
     RollShared *sh = reinterpret_cast<RollShared *>(smem + t.off_queue);
@@ -529,9 +732,14 @@ __device__ __forceinline__ void rollout_cta(const DevCfg &c, const RollArgs &ra,
         else if (lane == 0) atomicAdd(&sh->done_slots, 1u);
     }
     __syncthreads();
-    if (warp < 2) roll_scene_warp<NW, RPL, OBS, SPW>(c, ra, smem, warp);
-    else if (warp < 2 + NB) roll_worker<NW, RPL, SPW>(c, ra, smem);
-    else roll_writer(ra, smem);
+    // Role by warp index.  The SM sub-partition's arbiter picks the eligible warp with the HIGHEST warp id
+    // first: the scene warps, whose dependent instruction chains are the critical path of every scene, get
+    // the highest ids of the CTA, the BFS workers and the record writer (throughput work with slack) the
+    // lowest.  (With the scene warps at ids 0 / 1 every instruction of theirs waited for the workers' BFS
+    // loops on the same sub-partition: ~5.7 cycles per instruction in the row-DP loop.)
+    if (warp < NB) roll_worker<NW, RPL, SPW>(c, ra, smem);
+    else if (warp == NB) roll_writer(ra, smem);  // (also without observations: it unpacks act / reward / done / plen)
+    else roll_scene_warp<NW, RPL, OBS, SPW, MODE>(c, ra, smem, warp == NB + 2 ? 0 : 1);
 }
 
 }  // namespace agv
