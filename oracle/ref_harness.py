@@ -1,9 +1,10 @@
-"""Headless import of the LIVE Python reference (build container only).
+"""Headless import of the unmodified Python reference.
 
-TEST INFRASTRUCTURE ONLY.  /root/reference does not exist on the GPU box, so this
-module is used exclusively by tests/golden/make_golden.py (which writes the
-committed fixtures) and by the optional `-m "not gpu"` live-reference tests that
-skip when the checkout is absent.  Recipe: SURVEY.md App. B.1.
+TEST INFRASTRUCTURE ONLY.  Sources: /root/reference in the build container, or its copy under the
+git-ignored baseline/_ref/ (made by __graft_entry__.build(), travels to the GPU box).  Used by
+tests/golden/make_golden*.py (which write the committed fixtures), by the tests that drive the
+reference's own controllers against this package's Scene, and by `bench.py --impl reference`.
+Recipe: SURVEY.md App. B.1.
 """
 from __future__ import annotations
 
@@ -14,7 +15,16 @@ import random
 import sys
 import types
 
-REF_ROOT = os.environ.get("AGV_REFERENCE_ROOT", "/root/reference")
+def _default_root():
+    """the live checkout in the build container, else the copy vendored by __graft_entry__.build()"""
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for cand in ("/root/reference", os.path.join(here, "baseline", "_ref")):
+        if os.path.isdir(os.path.join(cand, "src", "multiAGVscene")):
+            return cand
+    return "/root/reference"
+
+
+REF_ROOT = os.environ.get("AGV_REFERENCE_ROOT") or _default_root()
 
 
 def available() -> bool:

@@ -212,18 +212,23 @@ class BatchedScene:
             self.host_join()
         return {"act": hb["act"], "reward": hb["reward"], "done": hb["done"], "obs": obs, "next_obs": nxt}
 
-    def collect_expert(self, replay, n_ticks: int, obs_kind=L.OBS_CLIP):
+    def collect_expert(self, replay, n_ticks: int, obs_kind=L.OBS_CLIP, ticks_per_launch: int = 8):
         """Expert-mode rollout collection (ExpertManager.create_data_by_self, batched): `n_ticks`
-        passes of the A_star control mode for every scene; each AGV turn's (state, A* action)
-        pair goes straight from the tick's output tensors into the device replay buffer
-        (reward / next state are stored too, so the same rows also serve DQN-style learners).
-        Returns the number of AGV turns pushed (device tensor)."""
+        passes of the A_star control mode for every scene, `ticks_per_launch` at a time in one
+        agv_rollout launch; the (state, A* action) pair of every AGV turn -- reward and next state
+        too, so the same rows also serve DQN-style learners -- goes from the rollout's rings into the
+        device replay buffer with ONE push per launch (rows in [tick, scene, agv] order, i.e. exactly
+        the order of per-tick pushes).  Returns the number of AGV turns pushed (device tensor)."""
         turns = torch.zeros((), dtype=torch.int64, device=self.device)
-        for _ in range(n_ticks):
-            o = self.tick(L.PROTO_ASTAR, L.POLICY_ASTAR, obs_kind, want_next=True, want_lens=False)
-            replay.push(o["act"].view(-1), o["reward"].view(-1), o["done"].view(-1),
-                        o["obs"].view(self.E * self.N, -1), o["next_obs"].view(self.E * self.N, -1), None)
+        done_ticks = 0
+        while done_ticks < n_ticks:
+            K = min(int(ticks_per_launch), n_ticks - done_ticks)
+            o = self.rollout(K, L.PROTO_ASTAR, L.POLICY_ASTAR, obs_kind, want_next=True, want_lens=False)
+            rows = K * self.E * self.N
+            replay.push(o["act"].view(-1), o["reward"].view(-1), o["done"].view(-1), o["obs"].view(rows, -1),
+                        o["next_obs"].view(rows, -1), None)
             turns += (o["act"] >= 0).sum()
+            done_ticks += K
         return turns
 
     # ------------------------------------------------------------------ sub-step protocol
@@ -273,6 +278,18 @@ class BatchedScene:
         assert hdr.shape == (self.E, 6) and agv.shape == (self.E, self.N, 8)
         L.check(self.lib.agv_set_state(self._h, hdr.ctypes.data_as(C.c_void_p), agv.ctypes.data_as(C.c_void_p),
                                        self._stream()), "agv_set_state")
+
+    def dump_frame(self, e: int = 0):
+        """Off-device frame of scene `e` for a viewer (the optional rendering hook of SURVEY 8f rank 4;
+        the pygame renderer itself, Scene.py:177-339, is out of scope): the `all_info` list of
+        Scene.create_info (Scene.py:341-352) -- [layout codes, [name, [x, y], [tx, ty], loaded], ...] for the
+        created AGVs -- plus the tick counter and the episode-over flag."""
+        hdr, agv = self.get_state()
+        info = [self.grid.tolist()]
+        for j in range(int(hdr[e, 4])):
+            x, y, tx, ty, _stage, loaded = (int(v) for v in agv[e, j, :6])
+            info.append(["veh%d" % (j + 1), [x, y], [tx, ty], bool(loaded)])
+        return {"all_info": info, "running_time": int(hdr[e, 0]), "task_finished": bool(hdr[e, 3]), "over": bool(hdr[e, 5])}
 
     def counters(self):
         """(AGV turns, episodes ended, invalid action codes) since the last call."""

@@ -922,6 +922,10 @@ int agv_set_state(AgvHandle *h, const int64_t *hdr_host, const int32_t *agv_host
     for (int e = 0; e < d.E; e++) {
         uint8_t *blk = h->h_state.data() + (size_t)e * d.env_stride;
         const int64_t *i6 = hdr_host + 6 * (size_t)e;
+        // the kernels index pos[j] for j < n_created and tasks[order]: a snapshot outside these ranges would
+        // read out of bounds instead of failing
+        if (i6[0] < 0 || i6[1] < 0 || i6[1] > d.T || i6[2] < 0 || i6[2] > d.T || i6[4] < 0 || i6[4] > d.N)
+            return AGV_E_INVALID;
         EnvHdr hd; memset(&hd, 0, sizeof(hd));
         hd.tick = (uint32_t)i6[0]; hd.cursor = (uint32_t)i6[1]; hd.n_done = (uint32_t)i6[2];
         hd.finished = (uint8_t)i6[3]; hd.n_created = (uint16_t)i6[4]; hd.over = (uint8_t)i6[5];
@@ -933,6 +937,7 @@ int agv_set_state(AgvHandle *h, const int64_t *hdr_host, const int32_t *agv_host
             const int32_t *a = agv_host + 8 * ((size_t)e * d.N + j);
             if (a[0] < 1 || a[0] > d.W || a[1] < 1 || a[1] > d.H || a[2] < 1 || a[2] > d.W || a[3] < 1 || a[3] > d.H)
                 return AGV_E_INVALID;
+            if (a[4] < 0 || a[4] > 2 || a[7] < 0 || a[7] >= (d.T > 0 ? d.T : 1)) return AGV_E_INVALID;
             pos[j] = (uint16_t)(a[0] | (a[1] << 8)); tgt[j] = (uint16_t)(a[2] | (a[3] << 8));
             meta[j] = (uint8_t)((a[4] & 3) | (a[5] ? 4 : 0) | (a[6] ? 8 : 0)); ord[j] = (uint16_t)a[7];
         }

@@ -270,15 +270,19 @@ def test_batched_agdqn_agent(pkg):
     turns = sum(int(agent.tick(train=True)) for _ in range(12))
     n_entries, _, total = agent.memory.info()
     assert turns > 0 and 0 < n_entries <= 4096 and total > 0
-    assert 12 * N - 2 <= agent.learn_step_counter <= 12 * N  # learning starts after 100 stored transitions
-    assert all(torch.isfinite(l) for l in agent.loss_value)
+    # learning starts once the replay really holds 100 entries (MADQN.py:131): within the first two ticks here
+    assert 10 * N <= agent.learn_step_counter <= 12 * N
+    assert agent.transitions_stored() == n_entries
+    import math
+    losses = agent.loss_value
+    assert len(losses) == agent.learn_step_counter and all(math.isfinite(l) and abs(l) <= 0.5 for l in losses)
     assert not torch.equal(w0, agent.policy_network.fc4.weight)
     # stored actions are network-indexable (a guidance STOP is never stored)
     bt = agent.memory.gather(torch.arange(n_entries))
     assert int(bt["act"].min()) >= 0 and int(bt["act"].max()) <= 3
     assert set(bt["obs"].float().unique().tolist()) <= {0.0, 1.0}
     # the reference Net layout: 1.74 M parameters, 2304-wide flatten
-    assert sum(p.numel() for p in M.Net().parameters()) == 1_739_908 or True
+    assert sum(p.numel() for p in M.Net().parameters()) == 1736516
     assert M.Net()(torch.zeros(2, 3, 7, 7)).shape == (2, 4)
     a.close()
     b.close()

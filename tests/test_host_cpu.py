@@ -12,7 +12,7 @@ import sys
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, ROOT, golden, load_pkg
+from conftest import GOLDEN, PKG_NAME, ROOT, golden, load_pkg
 
 
 def test_library_exports_every_declared_symbol():
@@ -158,3 +158,78 @@ def test_two_rank_sharding_and_reduction_gloo():
         p.join(timeout=60)
     assert [r[1:3] for r in res] == [(0, 5), (5, 10)]
     assert all(r[3] == 11.0 and r[4] == 300 for r in res)
+
+
+def test_checkpoint_aliases_pickle_under_the_reference_class_path(tmp_path):
+    """whole-module pickles are written under the reference's class path and load back without the
+    reference on sys.path (algorithm/checkpoint.py); CPU only"""
+    import importlib
+    import zipfile
+    import torch
+    ck = importlib.import_module(PKG_NAME + ".algorithm.checkpoint")
+    M = importlib.import_module(PKG_NAME + ".algorithm.MADQN_structure.MADQN")
+    torch.manual_seed(1)
+    net = M.Net()
+    p = str(tmp_path / "policy_net.pt")
+    ck.save_module(net, p)
+    z = zipfile.ZipFile(p)
+    blob = z.read([n for n in z.namelist() if n.endswith("data.pkl")][0])
+    assert b"algorithm.MADQN_structure.MADQN" in blob and PKG_NAME.encode() not in blob
+    assert "algorithm.MADQN_structure.MADQN" not in sys.modules  # the aliases are gone again
+    back = ck.load_module(p)
+    x = torch.rand(3, 3, 7, 7)
+    assert torch.equal(net(x), back(x))
+    D = importlib.import_module(PKG_NAME + ".algorithm.DQN_structure.DQN")
+    dnet = D.Net(3, 5, 7, 6)
+    p2 = str(tmp_path / "dqn.pt")
+    ck.save_module(dnet, p2, ref_module="DQN_structure.DQN")
+    assert torch.equal(ck.load_module(p2)(torch.zeros(1, 3, 6, 7)), dnet(torch.zeros(1, 3, 6, 7)))
+
+
+def _grad_worker(rank, world, port, q):
+    import importlib
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    M = importlib.import_module(PKG_NAME + ".algorithm.MADQN_structure.MADQN")
+    torch.manual_seed(0)
+    pol, tgt = M.Net(), M.Net()
+    g = torch.Generator().manual_seed(5)
+    B = 16
+    obs = (torch.rand(B, 3, 7, 7, generator=g) > 0.5).float()
+    nxt = (torch.rand(B, 3, 7, 7, generator=g) > 0.5).float()
+    act = torch.randint(0, 4, (B, 1), generator=g)
+    rew = torch.randint(-1, 2, (B, 1), generator=g).float()
+    done = (torch.rand(B, 1, generator=g) > 0.8).float()
+    lo, hi = rank * B // world, (rank + 1) * B // world
+    loss = M.ddqn_loss(pol, tgt, obs[lo:hi], act[lo:hi], rew[lo:hi], nxt[lo:hi], done[lo:hi], 0.95, torch.nn.SmoothL1Loss())
+    loss.backward()
+    flat = torch.cat([p.grad.reshape(-1) for p in pol.parameters()])
+    dist.all_reduce(flat)
+    flat /= world                       # BatchedAgent._adagrad_step: mean over ranks of the flat gradient
+    if rank == 0:
+        pol.zero_grad()
+        M.ddqn_loss(pol, tgt, obs, act, rew, nxt, done, 0.95, torch.nn.SmoothL1Loss()).backward()
+        full = torch.cat([p.grad.reshape(-1) for p in pol.parameters()])
+        q.put(float((flat - full).abs().max() / full.abs().max()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_mean_equals_single_rank_gradient():
+    """the multi-rank learner's gradient -- per-rank DDQN loss on its half of the batch, all-reduced flat
+    gradient divided by the world size -- equals the single-rank gradient on the concatenated batch
+    (world_size 2, gloo, CPU)"""
+    import multiprocessing as mp
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    err = q.get(timeout=300)
+    for p in ps:
+        p.join(timeout=120)
+    assert err < 1e-5, err
