@@ -194,8 +194,9 @@ class CpuArm:
 def _pyref_worker(q_out, root, workload, seed, seconds):
     """one process = one core: the UNMODIFIED Python reference (Scene / Explorer / Layout / StateManager /
     astar, imported from the vendored copy with pygame / matplotlib stubbed) driven in 'intelligent' mode by
-    an A*-guidance controller that builds the limited-visual state in both callbacks (SURVEY 8d, App. B.5);
-    counts execute_action calls for `seconds` of wall time."""
+    an A*-guidance controller that builds the limited-visual state of the acting AGV and takes the first
+    FindPathAstar action (what one GPU turn does: encode + guidance + execute_action; SURVEY 8d, App. B.5);
+    counts the turns taken in `seconds` of wall time."""
     import contextlib
     import io
     import random
@@ -322,8 +323,8 @@ def sub_train(pkg, lib, du, dev, local_rank, world, steps, matched=False):
     sc.reset()
     M = importlib.import_module(PKG + ".algorithm.MADQN_structure.MADQN")
     if matched:
-        agent = M.BatchedAgent(sc, memory_size=50000, batch_size=32, epsilon=0.8, ddp=world > 1, updates_per_substep=E,
-                               seed=rank)
+        agent = M.BatchedAgent(sc, memory_size=50000, batch_size=32, epsilon=0.8, ddp=world > 1, seed=rank,
+                               updates_per_transition=1.0)
     else:
         agent = M.BatchedAgent(sc, memory_size=1 << 20, batch_size=256, epsilon=0.8, ddp=world > 1, seed=rank)
     for _ in range(3 if matched else 2 * N + 4):
@@ -404,7 +405,9 @@ def main():
     ap.add_argument("--scenes", type=int, default=0, help="override scenes per GPU")
     ap.add_argument("--ticks", type=int, default=16, help="ticks per step (one agv_rollout launch); 0 = one agv_tick per step")
     ap.add_argument("--reps", type=int, default=5, help="repetitions of every timed window (the median is reported)")
-    ap.add_argument("--spinup", type=int, default=-1, help="untimed ticks before warm-up (default: 2*AGVs)")
+    ap.add_argument("--spinup", type=int, default=-1,
+                    help="untimed ticks before warm-up (default: 6*AGVs -- the scenes all start at Scene.init and the "
+                         "workload swings for ~250 ticks before it is stationary: tuning/drift.py)")
     ap.add_argument("--mode", default="env", choices=["env", "train", "train-matched", "expert", "substep"],
                     help="env: the headline (+ train / expert sub-records); train / expert: one sub-record alone; "
                          "substep: the per-AGV callback protocol (encode -> step per AGV index) replayed from one CUDA "
@@ -457,8 +460,8 @@ def main():
             v = turns / max(secs, 1e-9)
             base = {"value": v, "unit": UNIT, "cores": nthr, "kind": "reference",
                     "sample": "unmodified Python Scene/Explorer/StateManager/astar from %s: %d processes x %.1f s of "
-                              "'intelligent' episodes with an A*-guidance controller (2 limited-visual encodes + "
-                              "FindPathAstar per AGV-step) per step, %d steps, %d AGV-steps" % (
+                              "'intelligent' episodes with an A*-guidance controller (one limited-visual encode + "
+                              "one FindPathAstar per AGV-step, like the GPU step) per step, %d steps, %d AGV-steps" % (
                                   os.path.relpath(py.root, ROOT) if py.root.startswith(ROOT) else py.root, nthr,
                                   args.ref_seconds, steps, turns)}
             ms_step = 1e3 * secs / steps
@@ -573,7 +576,7 @@ def main():
             sc.tick(PROTO, POL, OBS, want_lens=False, out=out)
 
     KK = max(1, K)
-    spin = args.spinup if args.spinup >= 0 else 2 * N
+    spin = args.spinup if args.spinup >= 0 else 6 * N
     for _ in range((spin + KK - 1) // KK):
         step()
     for _ in range(warmup):

@@ -171,7 +171,8 @@ class Agent:
 class BatchedAgent:
     def __init__(self, scene, policy_net=None, target_net=None, memory_size=1 << 20, batch_size=256,
                  start_training_info_number=100, gamma=0.95, lr=0.01, target_replace_iter=100, epsilon=0.8,
-                 updates_per_substep=1, autocast=True, ddp=False, seed=0, graph_learner=None):
+                 updates_per_substep=1, autocast=True, ddp=False, seed=0, graph_learner=None,
+                 updates_per_transition=None):
         self.scene = scene
         self.device = scene.device
         self.policy_network = (policy_net or Net()).to(self.device).to(memory_format=torch.channels_last)
@@ -194,7 +195,12 @@ class BatchedAgent:
         self.learn_step_counter = 0
         self.TARGET_REPLACE_ITER = target_replace_iter
         self.GAMMA = gamma
+        # learner schedule: a fixed number of updates per sub-step (default: 1, each on a batch drawn from all the
+        # scenes' transitions), or -- the reference's schedule, MADQN.py:131-132 -- `updates_per_transition`
+        # updates for every transition the sub-step stored (one synchronising count read per sub-step)
         self.updates_per_substep = updates_per_substep
+        self.updates_per_transition = updates_per_transition
+        self._upd_carry = 0.0
         self.memory = DeviceReplay(memory_size, (3, scene.K, scene.K), device=scene.device_index)
         # Adagrad(lr) with torch's defaults (lr_decay 0, eps 1e-10, accumulator 0), written as the same
         # three foreach ops torch.optim.Adagrad runs, so that the whole update can sit in a CUDA graph
@@ -295,7 +301,16 @@ class BatchedAgent:
                     dist.all_reduce(n, op=dist.ReduceOp.MIN)
                 self._learning = n.item() >= self.start_training_info_number
             if self._learning:
-                for _ in range(self.updates_per_substep):
+                n_upd = self.updates_per_substep
+                if self.updates_per_transition is not None:
+                    cnt = storable.sum().float().reshape(1)
+                    if self.world > 1:  # the ranks' update counts must agree (one all-reduce per update)
+                        import torch.distributed as dist
+                        dist.all_reduce(cnt, op=dist.ReduceOp.MAX)
+                    self._upd_carry += float(cnt.item()) * self.updates_per_transition
+                    n_upd = int(self._upd_carry)
+                    self._upd_carry -= n_upd
+                for _ in range(n_upd):
                     self.update_network()
         self.finish_update()
         sc.end_tick()

@@ -162,7 +162,7 @@ __device__ __forceinline__ void tick_async(const DevCfg &c, const LaneArgs &t, u
         __threadfence_block();
     }
     named_bar_sync(3, 64);  // both scene warps: tables, scene blocks and default outputs are in place
-    if (ws.has) ws.has = ((ws.hdr_w[6] >= (unsigned)AGV_HEAVY_BFS) ? 1 : 0) == which;
+    if (ws.has) ws.has = (((ws.hdr_w[6] & 0xFFFFu) >= (unsigned)AGV_HEAVY_BFS) ? 1 : 0) == which;  // (high half: turns, agv_rollout.cuh)
     unsigned n_bfs = 0;
     bool live = ws.has;
     if (ws.has) {

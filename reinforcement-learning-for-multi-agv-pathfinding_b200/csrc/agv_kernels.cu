@@ -759,15 +759,30 @@ int agv_rollout(AgvHandle *h, int32_t n_ticks, int32_t proto, int32_t policy, in
     if (n_ticks == 0) return AGV_OK;
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     const int ok = (obs_dev || next_obs_dev) ? obs_kind : AGV_OBS_NONE;
+    const size_t per = (size_t)h->cfg.E * h->cfg.N, R = (size_t)obs_elems(h, ok);
     const char *e = getenv("AGV_ROLLOUT_IMPL");  // "ticks" forces the per-tick fallback (A/B runs, tests)
     if (!(e && strcmp(e, "ticks") == 0)) {
-        const int rc = rollout_launch(h, n_ticks, proto, policy, ok, action_dev, act_out_dev, reward_dev, done_dev,
-                                      plen_dev, slen_dev, obs_dev, next_obs_dev, (cudaStream_t)stream);
+        // Long rollouts are taken in chunks of at most 16 ticks per launch (AGV_ROLLOUT_CHUNK): it bounds the
+        // per-turn scratch, and every launch re-sorts the scenes longest-first and re-deals them over the CTAs.
+        // Measured at c3 in steady state, 16 ticks: 16 per launch 1.175e9, 4: 1.167e9, 2: 1.12e9, 1: 1.05e9
+        // AGV-steps/s.  Same results for every chunk size.
+        static const int chunk_env = getenv("AGV_ROLLOUT_CHUNK") ? atoi(getenv("AGV_ROLLOUT_CHUNK")) : 0;
+        const int chunk = chunk_env > 0 ? chunk_env : 16;
+        int rc = AGV_OK;
+        for (int k0 = 0; k0 < n_ticks && rc == AGV_OK; k0 += chunk) {
+            const size_t o = per * (size_t)k0;
+            rc = rollout_launch(h, n_ticks - k0 < chunk ? n_ticks - k0 : chunk, proto, policy, ok,
+                                action_dev ? action_dev + o : nullptr, act_out_dev ? act_out_dev + o : nullptr,
+                                reward_dev ? reward_dev + o : nullptr, done_dev ? done_dev + o : nullptr,
+                                plen_dev ? plen_dev + o : nullptr, slen_dev ? slen_dev + o : nullptr,
+                                obs_dev ? (void *)((uint16_t *)obs_dev + o * R) : nullptr,
+                                next_obs_dev ? (void *)((uint16_t *)next_obs_dev + o * R) : nullptr, (cudaStream_t)stream);
+            if (rc == AGV_E_UNSUPPORTED && k0 > 0) return AGV_E_CUDA;  // (cannot happen: support depends on the configuration only)
+        }
         if (rc != AGV_E_UNSUPPORTED) return rc;
     }
     // configurations the persistent kernel does not cover (shaped reward, full-map observations,
     // K != 7): n_ticks launches of the fused tick, each writing its slice of the rings
-    const size_t per = (size_t)h->cfg.E * h->cfg.N, R = (size_t)obs_elems(h, ok);
     for (int k = 0; k < n_ticks; k++) {
         const size_t o = per * (size_t)k;
         const int rc = agv_tick(h, proto, policy, obs_kind, action_dev ? action_dev + o : nullptr,

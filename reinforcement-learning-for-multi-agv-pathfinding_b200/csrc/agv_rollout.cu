@@ -18,16 +18,21 @@ k_rollout(const DevCfg c, const RollArgs ra) {
     rollout_cta<NW, RPL, OBS, SPW, NB, MODE>(c, ra, lane_smem);
 }
 
-// Heaviest-first scene order: counting sort of the scenes by the BFS count of their last tick (scene
-// header word 6, clipped to 63), heaviest bucket first.  One CTA; the order inside a bucket does not
-// matter (scenes are independent: the schedule never changes a result).
+// Longest-first scene order: counting sort of the scenes by the length of their last tick -- turns taken
+// plus BFS searches (a BFS round trip costs about as much as a turn), scene header word 6 = BFS count |
+// turns << 16 -- in 64 buckets, longest first.  One CTA; the order inside a bucket does not matter (scenes
+// are independent: the schedule never changes a result).
+__device__ __forceinline__ unsigned order_bucket(unsigned w) {
+    return 63u - min(((w & 0xFFFFu) + (w >> 16)) >> 1, 63u);
+}
+
 __global__ void __launch_bounds__(1024) k_rollout_order(const DevCfg c, unsigned *order, unsigned *qctr, unsigned q0) {
     __shared__ unsigned hist[64], base[64];
     if (threadIdx.x < 64) hist[threadIdx.x] = 0u;
     __syncthreads();
     for (int e = threadIdx.x; e < c.E; e += blockDim.x) {
         const unsigned w = *reinterpret_cast<const unsigned *>(c.state + (size_t)e * c.env_stride + 24);
-        atomicAdd(&hist[63u - min(w, 63u)], 1u);
+        atomicAdd(&hist[order_bucket(w)], 1u);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -38,7 +43,7 @@ __global__ void __launch_bounds__(1024) k_rollout_order(const DevCfg c, unsigned
     __syncthreads();
     for (int e = threadIdx.x; e < c.E; e += blockDim.x) {
         const unsigned w = *reinterpret_cast<const unsigned *>(c.state + (size_t)e * c.env_stride + 24);
-        order[atomicAdd(&base[63u - min(w, 63u)], 1u)] = (unsigned)e;
+        order[atomicAdd(&base[order_bucket(w)], 1u)] = (unsigned)e;
     }
 }
 
@@ -86,10 +91,12 @@ static int launch_rollout(const DevCfg &dc, RollArgs ra, unsigned *order, cudaSt
         cps_cached = n;
         smem_cached = smem;
     }
-    // persistent CTAs: at most `cps` per SM (AGV_ROLLOUT_CPS lowers it: fewer resident scenes, each running
-    // faster, the rest waiting in the queue), never more than the scenes need
+    // Persistent CTAs, never more than the scenes need.  One CTA slot per SM is left free when there are three
+    // or more: co-resident CTAs slow each other's dependent turn chains more than the scene queue costs
+    // (c3, 16384 scenes on 148 SMs: 4 per SM = all scenes resident, 1.10e9 AGV-steps/s; 3 per SM = 13 % of the
+    // scenes -- the shortest ones -- wait in the queue, 1.15e9; 2 per SM 0.97e9).  AGV_ROLLOUT_CPS overrides.
     int cps = env_int("AGV_ROLLOUT_CPS", 0);
-    if (cps < 1 || cps > cps_cached) cps = cps_cached;
+    if (cps < 1 || cps > cps_cached) cps = cps_cached >= 3 ? cps_cached - 1 : cps_cached;
     int ctas = (dc.E + SPW - 1) / SPW;
     if (ctas > sms * cps) ctas = sms * cps;
     k_rollout_order<<<1, 1024, 0, st>>>(dc, order, ra.qctr, (unsigned)ctas * SPW);

@@ -86,8 +86,13 @@ struct RollShared {
 };
 
 constexpr int LS_IDLE = 4, LS_NEWTICK = 5, LS_TICKEND = 6;
+#ifndef AGV_ROLL_LIGHT_BFS
+#define AGV_ROLL_LIGHT_BFS 8
+#endif
 #ifndef AGV_ROLL_SLOW_EVERY
-#define AGV_ROLL_SLOW_EVERY 4   // power of two: the light scene warp runs its slow section every n-th iteration
+#define AGV_ROLL_SLOW_EVERY 1   // power of two: the light scene warp runs its slow section every n-th iteration
+                                // (measured at c3: 1 -> 1.125e9, 2 -> 1.12e9, 4 -> 1.10e9, 8 -> 1.0e9 AGV-steps/s: what the
+                                // fast iterations save, the scenes waiting at their tick boundary lose)
 #endif
 
 // lane_monotone (agv_lanes.cuh) reshaped for the latency of ONE warp (nothing else runs on the scene warp's
@@ -223,7 +228,7 @@ __device__ __forceinline__ void roll_load_slot(const DevCfg &c, const LaneArgs &
         sh->slot_e[slot] = e;
         sh->slot_k[slot] = 0;
         sh->slot_fl[slot] = bits != n_created ? 1u : 0u;
-        const unsigned heavy = blk[6] >= (unsigned)AGV_HEAVY_BFS ? 1u : 0u;
+        const unsigned heavy = (blk[6] & 0xFFFFu) >= (unsigned)AGV_HEAVY_BFS ? 1u : 0u;
         __threadfence_block();
         *reinterpret_cast<volatile unsigned *>(&sh->ctl[slot]) = 2u + heavy;
     }
@@ -439,7 +444,8 @@ __device__ __forceinline__ void roll_scene_warp(const DevCfg &c, const RollArgs 
     ws.over = 1; ws.finished = 0; ws.n_created = 0; ws.tick = 0; ws.cursor = 0; ws.n_done = 0; ws.acted_mask = 0;
 
     int st = LS_IDLE, i = 0, n_loop = 0, k = 0;
-    unsigned n_bfs = 0;     // BFS searches of the tick in progress (weight of the scene once the tick is over)
+    unsigned n_bfs = 0;     // BFS searches of the tick in progress ...
+    unsigned n_turns = 0;   // ... and turns of the last finished tick: the scene's weight in the next launch's order
     unsigned rec0 = 0;      // (k * E + e) * N: first output record of the scene's tick in progress
     unsigned head = 0, it = 0;
     Agv a;
@@ -477,7 +483,8 @@ __device__ __forceinline__ void roll_scene_warp(const DevCfg &c, const RollArgs 
                 ws.prefetch_cursor_task();
                 k = *reinterpret_cast<volatile int *>(&sh->slot_k[lane]);
                 ws.overlap = (*reinterpret_cast<volatile unsigned *>(&sh->slot_fl[lane]) & 1u) != 0u;
-                n_bfs = ws.hdr_w[6];
+                n_bfs = ws.hdr_w[6] & 0xFFFFu;
+                n_turns = ws.hdr_w[6] >> 16;
                 vctl[lane] = (unsigned)which;
                 st = LS_NEWTICK;
                 RPROF(if (ra.prof) { if (k == 0) ra.prof[(size_t)ws.e * 8 + 4] = roll_now(); atomicAdd(ra.prof + (size_t)ws.e * 8 + 5, 1ull); })
@@ -486,6 +493,7 @@ __device__ __forceinline__ void roll_scene_warp(const DevCfg &c, const RollArgs 
             // record writer: {first record, who took a turn}
             const bool tick_end = st == LS_TICKEND;
             if (tick_end) {
+                n_turns = (unsigned)__popcll(ws.acted_mask);
                 if (!ws.over) ws.spawn();
                 k++;
                 st = LS_NEWTICK;
@@ -508,15 +516,18 @@ __device__ __forceinline__ void roll_scene_warp(const DevCfg &c, const RollArgs 
             }
             // ---- start of a tick
             if (st == LS_NEWTICK) {
-                const int w_new = n_bfs >= (unsigned)AGV_HEAVY_BFS ? 1 : 0;
+                // hysteresis: a scene goes to the heavy warp at AGV_HEAVY_BFS searches per tick and returns below
+                // AGV_ROLL_LIGHT_BFS (scenes around the threshold otherwise change warps every other tick, and in the
+                // light warp every BFS costs them a whole -- long -- iteration)
+                const int w_new = n_bfs >= (unsigned)(which ? AGV_ROLL_LIGHT_BFS : AGV_HEAVY_BFS) ? 1 : 0;
                 if (k >= K) {          // this scene is through: a worker stores it and fetches the next one
-                    ws.regs_to_hdr(); ws.hdr_w[6] = n_bfs;
+                    ws.regs_to_hdr(); ws.hdr_w[6] = n_bfs | (n_turns << 16);
                     __threadfence_block();
                     vs[lane] = 4u;
                     st = LS_IDLE;
                     RPROF(if (ra.prof) { ra.prof[(size_t)ws.e * 8 + 0] = roll_now(); ra.prof[(size_t)ws.e * 8 + 6] = blockIdx.x; })
                 } else if (w_new != which) {  // its last tick was heavy (light): continue on the other scene warp
-                    ws.regs_to_hdr(); ws.hdr_w[6] = n_bfs;
+                    ws.regs_to_hdr(); ws.hdr_w[6] = n_bfs | (n_turns << 16);
                     sh->slot_k[lane] = k; sh->slot_fl[lane] = ws.overlap ? 1u : 0u;
                     __threadfence_block();
                     vctl[lane] = 2u + (unsigned)w_new;
@@ -665,22 +676,26 @@ __device__ __forceinline__ void roll_scene_warp(const DevCfg &c, const RollArgs 
             const int ma = lane_monotone_pf<NW>(need, ws.tab, ws.HN, om ? ws.occ : zr, om ? ws.occm : zr, a.loaded, sx, sy,
                                                 tx, ty, l);
             RQ(7)
+            bool want_bfs = false;
             if (need) {
                 if (ma >= 0) {
                     action = ma; plen = l; st = LS_HAVE;
                     if (MODE != 1 && guard) { ws.occ_clear(0, 0); guard = false; }
                     // about to reach the target: the task word of the next stage will be needed on the chain
                     if (l <= 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(ws.tasks_e + a.order));
-                } else {  // level-synchronous BFS by a worker warp; this scene waits, the others go on
-                    *reinterpret_cast<volatile unsigned *>(&sh->bfs_req[lane]) =
-                        (unsigned)sx | ((unsigned)sy << 7) | ((unsigned)tx << 14) | ((unsigned)ty << 21) |
-                        ((unsigned)a.loaded << 28) | (om ? (1u << 29) : 0u);
-                    __threadfence_block();
-                    vs[lane] = 1u;
-                    st = LS_WAIT;
-                    n_bfs++;
-                    RPROF(t_post = clock64();)
-                }
+                } else want_bfs = true;   // no Manhattan-length path: the level-synchronous BFS decides
+            }
+            const unsigned pk = (unsigned)sx | ((unsigned)sy << 7) | ((unsigned)tx << 14) | ((unsigned)ty << 21) |
+                                ((unsigned)a.loaded << 28) | (om ? (1u << 29) : 0u);
+            // (Letting the heavy warp run one pending search itself -- no hand-off -- was measured: -15 %; its other
+            // scenes, whose answers are ready, then wait for that search.)
+            if (want_bfs) {  // by a worker warp; this scene waits, the others go on
+                *reinterpret_cast<volatile unsigned *>(&sh->bfs_req[lane]) = pk;
+                __threadfence_block();
+                vs[lane] = 1u;
+                st = LS_WAIT;
+                n_bfs++;
+                RPROF(t_post = clock64();)
             }
         }
         RQ(6)

@@ -15,6 +15,8 @@ out = {}
 for _ in range(2 * N // 16 + 1):
     sc.rollout(16, pkg.PROTO_INTELLIGENT, pkg.POLICY_GUIDED, pkg.OBS_CLIP, want_lens=False, out=out)
 out = {}
+for _ in range(2):
+    sc.rollout(K, pkg.PROTO_INTELLIGENT, pkg.POLICY_GUIDED, pkg.OBS_CLIP, want_lens=False, out=out)
 for rep in range(2):
     sc.counters()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -40,7 +42,14 @@ for q in (0.25, 0.5, 0.75, 0.9, 0.95, 0.99):
     print("  at %.0f%% of the kernel (%.2f ms): %5d scenes still running" % (q * 100, tq, ((start <= tq) & (fin > tq)).sum()))
 bfs, trn, wait, plen = p[:, 1], p[:, 2], p[:, 3], p[:, 7]
 print("per scene over K ticks: bfs mean %.1f max %d; turns mean %.0f; wait cycles/bfs mean %.0f" % (bfs.mean(), bfs.max(), trn.mean(), wait.sum() / max(1, bfs.sum())))
-order = np.argsort(-dur)[:12]
+# per-CTA finish time (its slowest scene) and how the load spread over CTAs
+cta = p[:, 6]
+last = np.zeros(int(cta.max()) + 1)
+np.maximum.at(last, cta, fin)
+print("CTA finish ms: mean %.3f p10 %.3f p50 %.3f p90 %.3f max %.3f" % (last.mean(), np.percentile(last, 10), np.median(last), np.percentile(last, 90), last.max()))
+late = fin > np.percentile(fin, 99)
+print("latest 1%% of scenes: turns mean %.0f (all %.0f), bfs mean %.1f (all %.1f), pickups mean %.2f, start mean %.3f ms" % (trn[late].mean(), trn.mean(), bfs[late].mean(), bfs.mean(), p[late, 5].mean(), start[late].mean()))
+order = np.argsort(-fin)[:12]
 for e in order:
     print("  scene %5d: dur %.3f ms (start %.3f) bfs %4d (%.1f/tick) turns %4d wait %.3f ms (%.0f cyc/bfs, mean plen %.0f) own %.0f cyc/turn  pickups %d cta %d" % (
         e, dur[e], start[e], bfs[e], bfs[e] / K, trn[e], wait[e] / 1.965e6, wait[e] / max(1, bfs[e]), plen[e] / max(1, bfs[e]),
