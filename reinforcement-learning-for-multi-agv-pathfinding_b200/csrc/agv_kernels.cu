@@ -484,6 +484,14 @@ static int rollout_launch(AgvHandle *h, int n_ticks, int proto, int policy, int 
     const size_t per_tick = (size_t)d.E * d.N, n = per_tick * (size_t)n_ticks;
     if (n >= (1ull << 31)) return AGV_E_UNSUPPORTED;
     if (d.shaped || !(obs_kind == AGV_OBS_NONE || (obs_kind == AGV_OBS_CLIP && d.K == 7))) return AGV_E_UNSUPPORTED;
+    // maps up to 32 rows x 64 columns: the warp-per-scene fused tick (grid in registers, BFS in the scene's own
+    // warp) is faster than lane-per-scene with BFS hand-offs -- README 9x9, 4 AGVs, 4096 scenes: 5.1e8 AGV-steps/s
+    // as 32 fused ticks per call against 3.0e8 in the persistent kernel.  AGV_ROLLOUT_IMPL=persistent forces the
+    // persistent kernel (tests run it on every shape).
+    {
+        const char *e = getenv("AGV_ROLLOUT_IMPL");
+        if (h->NW == 1 && h->RPL == 1 && !(e && strcmp(e, "persistent") == 0)) return AGV_E_UNSUPPORTED;
+    }
     if (!h->d_order) {
         CUDA_TRY(cudaMalloc(&h->d_order, sizeof(unsigned) * (size_t)d.E));
         CUDA_TRY(cudaMalloc(&h->d_qctr, sizeof(unsigned)));

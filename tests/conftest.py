@@ -39,4 +39,6 @@ def tick_impl(request, monkeypatch):
     persistent rollout kernel with n_ticks = 1 (agv_rollout.cuh).
     The library reads AGV_TICK_IMPL at every call."""
     monkeypatch.setenv("AGV_TICK_IMPL", request.param)
+    if request.param == "rollout":
+        monkeypatch.setenv("AGV_ROLLOUT_IMPL", "persistent")  # also on the small maps agv_rollout would not take
     return request.param

@@ -610,6 +610,7 @@ def test_cross_implementation_fuzz(pkg, seed, monkeypatch):
     policy = [pkg.POLICY_GIVEN, pkg.POLICY_GUIDED, pkg.POLICY_ASTAR][seed % 3]
     want_next = bool(seed % 4 == 1)
     results = {}
+    monkeypatch.setenv("AGV_ROLLOUT_IMPL", "persistent")
     for impl in ("warp", "lanes", "async", "rollout"):
         monkeypatch.setenv("AGV_TICK_IMPL", impl)
         sc = pkg.BatchedScene(grid, E, N, tasks=tasks, P=3, auto_reset=True)

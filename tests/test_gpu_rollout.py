@@ -19,6 +19,15 @@ def pkg():
     return load_pkg()
 
 
+@pytest.fixture(autouse=True, params=["persistent", "default"])
+def rollout_impl(request, monkeypatch):
+    """every test runs twice: with the persistent kernel forced on every map shape, and with the library's
+    own choice (maps up to 32 x 64 take the per-tick path inside agv_rollout)"""
+    if request.param == "persistent":
+        monkeypatch.setenv("AGV_ROLLOUT_IMPL", "persistent")
+    return request.param
+
+
 def _np(o, key):
     return o[key].cpu().numpy()
 
