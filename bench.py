@@ -421,6 +421,9 @@ def main():
     ap.add_argument("--no-sub", action="store_true", help="skip the train / expert sub-records")
     ap.add_argument("--shaped", action="store_true", help="settings.Sparse_Reward shaped reward (a second path search per turn)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--given", action="store_true",
+                    help="device-timed leg with POLICY_GIVEN and an all -1 action tensor resident on the device (what the "
+                         "e2e legs run, minus the copies)")
     ap.add_argument("--ref-seconds", type=float, default=4.0, help="--impl reference: seconds of Python scene per step and core")
     args = ap.parse_args()
     steps, warmup = max(1, args.steps), max(3, args.warmup)
@@ -569,11 +572,14 @@ def main():
         return finish(line)
 
     # ------------------------------------------------------------------ headline: fused rollout steps
+    act_dev = torch.full((max(1, K), E, N) if K > 0 else (E, N), -1, dtype=torch.int8, device=dev) if args.given else None
+
     def step():
+        pol = pkg.POLICY_GIVEN if args.given else POL
         if K > 0:
-            sc.rollout(K, PROTO, POL, OBS, want_lens=False, out=out)
+            sc.rollout(K, PROTO, pol, OBS, actions=act_dev, want_lens=False, out=out)
         else:
-            sc.tick(PROTO, POL, OBS, want_lens=False, out=out)
+            sc.tick(PROTO, pol, OBS, actions=act_dev, want_lens=False, out=out)
 
     KK = max(1, K)
     spin = args.spinup if args.spinup >= 0 else 6 * N

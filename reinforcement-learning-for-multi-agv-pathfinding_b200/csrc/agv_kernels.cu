@@ -825,27 +825,42 @@ int agv_rollout_host(AgvHandle *h, int32_t n_ticks, int32_t proto, int32_t polic
         h->copy_pending[0] = h->copy_pending[1] = false;
         h->tick_pending[0] = h->tick_pending[1] = false;
     }
-    // same double-buffered pipeline as agv_tick_host: the upload of call k+1 and the copy-back of call
-    // k-1 overlap the rollout of call k
+    // Same double-buffered pipeline as agv_tick_host -- the upload of call k+1 and the copy-back of call k-1
+    // overlap the rollout of call k -- and, inside one call, the rollout runs in chunks of a few ticks
+    // (AGV_ROLLOUT_HOST_CHUNK, default 4) whose actions are uploaded and whose results are copied back while
+    // the neighbouring chunks compute: a caller that waits for every call (closed loop) sees the last chunk's
+    // copy-back only, not the whole ring's.
+    static const int hc_env = getenv("AGV_ROLLOUT_HOST_CHUNK") ? atoi(getenv("AGV_ROLLOUT_HOST_CHUNK")) : 0;
+    const int hc = hc_env > 0 ? hc_env : 4;
+    const size_t per = (size_t)h->cfg.E * h->cfg.N;
+    const int ok = (obs_dev || next_obs_dev) ? obs_kind : AGV_OBS_NONE;
+    const size_t R = (size_t)obs_elems(h, ok);
     const int b = h->roll_calls & 1;
     if (h->copy_pending[b]) CUDA_TRY(cudaStreamWaitEvent(st, h->ev_copy[b], 0));
     if (policy == AGV_POLICY_GIVEN) {
         if (!action_host) return AGV_E_INVALID;
         if (h->tick_pending[b]) CUDA_TRY(cudaStreamWaitEvent(h->h2d_stream, h->ev_tick[b], 0));
-        CUDA_TRY(cudaMemcpyAsync(h->r_action[b], action_host, n, cudaMemcpyHostToDevice, h->h2d_stream));
-        CUDA_TRY(cudaEventRecord(h->ev_h2d[b], h->h2d_stream));
-        CUDA_TRY(cudaStreamWaitEvent(st, h->ev_h2d[b], 0));
     }
-    const int rc = agv_rollout(h, n_ticks, proto, policy, obs_kind, policy == AGV_POLICY_GIVEN ? h->r_action[b] : nullptr,
-                               h->r_act_out[b], h->r_reward[b], h->r_done[b], nullptr, nullptr, obs_dev, next_obs_dev,
-                               stream);
-    if (rc != AGV_OK) return rc;
-    CUDA_TRY(cudaEventRecord(h->ev_tick[b], st));
+    for (int k0 = 0; k0 < n_ticks; k0 += hc) {
+        const int kc = n_ticks - k0 < hc ? n_ticks - k0 : hc;
+        const size_t o = per * (size_t)k0, nc = per * (size_t)kc;
+        if (policy == AGV_POLICY_GIVEN) {
+            CUDA_TRY(cudaMemcpyAsync(h->r_action[b] + o, action_host + o, nc, cudaMemcpyHostToDevice, h->h2d_stream));
+            CUDA_TRY(cudaEventRecord(h->ev_h2d[b], h->h2d_stream));
+            CUDA_TRY(cudaStreamWaitEvent(st, h->ev_h2d[b], 0));
+        }
+        const int rc = agv_rollout(h, kc, proto, policy, obs_kind, policy == AGV_POLICY_GIVEN ? h->r_action[b] + o : nullptr,
+                                   h->r_act_out[b] + o, h->r_reward[b] + o, h->r_done[b] + o, nullptr, nullptr,
+                                   obs_dev ? (void *)((uint16_t *)obs_dev + o * R) : nullptr,
+                                   next_obs_dev ? (void *)((uint16_t *)next_obs_dev + o * R) : nullptr, stream);
+        if (rc != AGV_OK) return rc;
+        CUDA_TRY(cudaEventRecord(h->ev_tick[b], st));
+        CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_tick[b], 0));
+        if (act_out_host) CUDA_TRY(cudaMemcpyAsync(act_out_host + o, h->r_act_out[b] + o, nc, cudaMemcpyDeviceToHost, h->copy_stream));
+        if (reward_host) CUDA_TRY(cudaMemcpyAsync(reward_host + o, h->r_reward[b] + o, nc * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
+        if (done_host) CUDA_TRY(cudaMemcpyAsync(done_host + o, h->r_done[b] + o, nc, cudaMemcpyDeviceToHost, h->copy_stream));
+    }
     h->tick_pending[b] = true;
-    CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_tick[b], 0));
-    if (act_out_host) CUDA_TRY(cudaMemcpyAsync(act_out_host, h->r_act_out[b], n, cudaMemcpyDeviceToHost, h->copy_stream));
-    if (reward_host) CUDA_TRY(cudaMemcpyAsync(reward_host, h->r_reward[b], n * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
-    if (done_host) CUDA_TRY(cudaMemcpyAsync(done_host, h->r_done[b], n, cudaMemcpyDeviceToHost, h->copy_stream));
     CUDA_TRY(cudaEventRecord(h->ev_copy[b], h->copy_stream));
     h->copy_pending[b] = true;
     h->roll_calls++;

@@ -121,6 +121,7 @@ static int dispatch_mode(const DevCfg &dc, const RollArgs &ra, unsigned *order, 
 #ifndef AGV_ROLL_GENERIC_ONLY
     if (t.proto == PROTO_INTELLIGENT && t.policy == POLICY_GUIDED) return launch_rollout<NW, RPL, OBS, 32, AGV_ROLL_NB, 1>(dc, ra, order, st);
     if (t.proto == PROTO_ASTAR && t.policy == POLICY_ASTAR) return launch_rollout<NW, RPL, OBS, 32, AGV_ROLL_NB, 2>(dc, ra, order, st);
+    if (t.proto == PROTO_INTELLIGENT && t.policy == POLICY_GIVEN) return launch_rollout<NW, RPL, OBS, 32, AGV_ROLL_NB, 3>(dc, ra, order, st);
 #endif
     return launch_rollout<NW, RPL, OBS, 32, AGV_ROLL_NB, 0>(dc, ra, order, st);
 }

@@ -415,7 +415,8 @@ __device__ __forceinline__ void roll_writer(const RollArgs &ra, uint8_t *smem) {
 
 // ------------------------------------------------------------------ scene warp
 // MODE fixes protocol and policy at compile time: 1 = "intelligent" + A* guidance (AG-DQN's guided branch,
-// the headline), 2 = A_star control mode (Expert rollouts), 0 = whatever the call says (open-loop actions).
+// the headline), 2 = A_star control mode (Expert rollouts), 3 = "intelligent" + per-AGV actions with the
+// guidance fallback (the epsilon-gate: what the host-buffer entry points run), 0 = whatever the call says.
 // The specialised kernels carry a third less code: a scene-warp iteration streams its whole body through
 // the 6 KB L0 / 32 KB L1.5 instruction caches once per turn, and instruction fetch was the top stall of the
 // generic body (ncu source view: stall_no_inst 37 % of the samples outside the row-DP loop).
@@ -435,8 +436,10 @@ __device__ __forceinline__ void roll_scene_warp(const DevCfg &c, const RollArgs 
     volatile unsigned *vdone_slots = &sh->done_slots;
     volatile unsigned *vhead = &sh->enc_head[which], *vtail = &sh->enc_tail[which];
     const int N = c.N, K = ra.K;
-    const int proto = MODE == 1 ? PROTO_INTELLIGENT : (MODE == 2 ? PROTO_ASTAR : t.proto);
-    const int policy = MODE == 1 ? POLICY_GUIDED : (MODE == 2 ? POLICY_ASTAR : t.policy);
+    constexpr bool GIVEN = MODE == 0 || MODE == 3;   // per-AGV actions from the caller (negative = guidance)
+    constexpr bool MAT_A = MODE == 0 || MODE == 2;   // searches on matrix (a) can occur ((1,1) guard while AGVs are uncreated)
+    const int proto = (MODE == 1 || MODE == 3) ? PROTO_INTELLIGENT : (MODE == 2 ? PROTO_ASTAR : t.proto);
+    const int policy = MODE == 1 ? POLICY_GUIDED : (MODE == 2 ? POLICY_ASTAR : (MODE == 3 ? POLICY_GIVEN : t.policy));
     const uint64_t om_a = N > 1 ? ~0ull : 0ull;
     const bool want_obs = OBS == OBS_CLIP && t.obs != nullptr, want_next = OBS == OBS_CLIP && t.next_obs != nullptr;
     const uint64_t *zr = reinterpret_cast<const uint64_t *>(smem + t.off_zero);
@@ -557,7 +560,7 @@ __device__ __forceinline__ void roll_scene_warp(const DevCfg &c, const RollArgs 
                 const unsigned r = *reinterpret_cast<volatile unsigned *>(&sh->bfs_res[lane]);
                 vs[lane] = 0u;
                 action = (int)(r & 0xFFu); plen = (int)(r >> 8);
-                if (MODE != 1 && guard) { ws.occ_clear(0, 0); guard = false; }
+                if (MAT_A && guard) { ws.occ_clear(0, 0); guard = false; }
                 st = LS_HAVE;
                 RPROF(if (ra.prof) { atomicAdd(ra.prof + (size_t)ws.e * 8 + 3, (unsigned long long)(clock64() - t_post)); atomicAdd(ra.prof + (size_t)ws.e * 8 + 7, (unsigned long long)plen); })
             }
@@ -571,7 +574,7 @@ __device__ __forceinline__ void roll_scene_warp(const DevCfg &c, const RollArgs 
         if (st == LS_HAVE) {
             const bool guided = (policy == POLICY_GUIDED) || (policy == POLICY_GIVEN && given < 0);
             const bool pol_a = !guided && policy == POLICY_ASTAR;
-            if (MODE == 0 && !guided && !pol_a && action > A_STOP) { ws.cnt_bad++; action = A_STOP; }
+            if (GIVEN && !guided && !pol_a && action > A_STOP) { ws.cnt_bad++; action = A_STOP; }
             const int dx = (action == A_RIGHT) - (action == A_LEFT);
             const int dy = (action == A_DOWN) - (action == A_UP);
             const int nx = a.x + dx, ny = a.y + dy;
@@ -637,7 +640,7 @@ __device__ __forceinline__ void roll_scene_warp(const DevCfg &c, const RollArgs 
         if (act) {
             a = ws.load_agv(i);
             given = -1;
-            if (MODE == 0 && policy == POLICY_GIVEN && t.action) {
+            if (GIVEN && policy == POLICY_GIVEN && t.action) {
                 // the action of the next AGV index was requested a turn ago (a global load here would
                 // put ~500 cycles of latency on every turn of the scene's chain)
                 given = (pf_idx == i) ? pf_val : (int)t.action[(size_t)rec0 + i];
@@ -658,7 +661,7 @@ __device__ __forceinline__ void roll_scene_warp(const DevCfg &c, const RollArgs 
             const bool guided = (policy == POLICY_GUIDED) || (policy == POLICY_GIVEN && given < 0);
             const bool pol_a = !guided && policy == POLICY_ASTAR;
             bool need = act && (guided || pol_a);
-            if (MODE == 0 && act && !need) { action = given; plen = 0; st = LS_HAVE; }
+            if (GIVEN && act && !need) { action = given; plen = 0; st = LS_HAVE; }
             const int sx = a.x - 1, sy = a.y - 1, tx = a.tx - 1, ty = a.ty - 1;
             if (need && sx == tx && sy == ty) { action = A_STOP; plen = 0; st = LS_HAVE; need = false; }
             // boxed in: none of the four neighbour cells is valid in matrix (b) -- they are cells 17, 23,
@@ -668,7 +671,7 @@ __device__ __forceinline__ void roll_scene_warp(const DevCfg &c, const RollArgs 
                 action = A_STOP; plen = 0; st = LS_HAVE; need = false;
             }
             // matrix (a) also blocks (1,1) while uncreated AGVs park there (Explorer.py:274-283)
-            if (MODE != 1 && need && pol_a && N > 1 && ws.n_created < N && !ws.occ_test(0, 0)) { ws.occ_set(0, 0); guard = true; }
+            if (MAT_A && need && pol_a && N > 1 && ws.n_created < N && !ws.occ_test(0, 0)) { ws.occ_set(0, 0); guard = true; }
             const uint64_t om = guided ? ~0ull : om_a;
             int l = 0;
             RPROF(rows_ += __reduce_max_sync(FULL, need ? abs(ty - sy) : 0);)
@@ -680,7 +683,7 @@ __device__ __forceinline__ void roll_scene_warp(const DevCfg &c, const RollArgs 
             if (need) {
                 if (ma >= 0) {
                     action = ma; plen = l; st = LS_HAVE;
-                    if (MODE != 1 && guard) { ws.occ_clear(0, 0); guard = false; }
+                    if (MAT_A && guard) { ws.occ_clear(0, 0); guard = false; }
                     // about to reach the target: the task word of the next stage will be needed on the chain
                     if (l <= 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(ws.tasks_e + a.order));
                 } else want_bfs = true;   // no Manhattan-length path: the level-synchronous BFS decides
