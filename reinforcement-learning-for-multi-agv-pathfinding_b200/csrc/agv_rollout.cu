@@ -111,19 +111,28 @@ static int launch_rollout(const DevCfg &dc, RollArgs ra, unsigned *order, cudaSt
 
 // protocol / policy specialisations (agv_rollout.cuh, MODE): the two modes the rollout exists for get their
 // own kernels; open-loop actions and mixed settings run on the generic one
-#ifndef AGV_ROLL_NB
-#define AGV_ROLL_NB 2   // BFS worker warps per CTA (measured at c3, 16 ticks: 2 -> 1.10e9, 3 -> 1.06e9, 4 -> 0.99e9 AGV-steps/s)
+// BFS worker warps per CTA.  64 x 64 (c3, 16 ticks): 2 -> 1.10e9, 3 -> 1.06e9, 4 -> 0.99e9 AGV-steps/s (the scene warps'
+// turn chains bind, more workers only compete for issue slots).  128 x 128 (c5, 8 ticks): searches are 4x longer
+// (4 rows x 2 words per lane, paths up to ~250 levels) and bind: 2 -> 2.08e8, 3 -> 2.31e8, 4 -> 2.44e8 (A_star
+// control mode 1.42e8 -> 1.89e8); 5 would not leave registers for 2 CTAs per SM.  AGV_ROLL_NB overrides (tuning).
+template <int NW, int RPL>
+constexpr int rollout_nb() {
+#ifdef AGV_ROLL_NB
+    return AGV_ROLL_NB;
+#else
+    return NW * RPL <= 2 ? 2 : (NW * RPL <= 4 ? 3 : 4);
 #endif
+}
 
 template <int NW, int RPL, int OBS>
 static int dispatch_mode(const DevCfg &dc, const RollArgs &ra, unsigned *order, cudaStream_t st) {
     const LaneArgs &t = ra.la;
 #ifndef AGV_ROLL_GENERIC_ONLY
-    if (t.proto == PROTO_INTELLIGENT && t.policy == POLICY_GUIDED) return launch_rollout<NW, RPL, OBS, 32, AGV_ROLL_NB, 1>(dc, ra, order, st);
-    if (t.proto == PROTO_ASTAR && t.policy == POLICY_ASTAR) return launch_rollout<NW, RPL, OBS, 32, AGV_ROLL_NB, 2>(dc, ra, order, st);
-    if (t.proto == PROTO_INTELLIGENT && t.policy == POLICY_GIVEN) return launch_rollout<NW, RPL, OBS, 32, AGV_ROLL_NB, 3>(dc, ra, order, st);
+    if (t.proto == PROTO_INTELLIGENT && t.policy == POLICY_GUIDED) return launch_rollout<NW, RPL, OBS, 32, rollout_nb<NW, RPL>(), 1>(dc, ra, order, st);
+    if (t.proto == PROTO_ASTAR && t.policy == POLICY_ASTAR) return launch_rollout<NW, RPL, OBS, 32, rollout_nb<NW, RPL>(), 2>(dc, ra, order, st);
+    if (t.proto == PROTO_INTELLIGENT && t.policy == POLICY_GIVEN) return launch_rollout<NW, RPL, OBS, 32, rollout_nb<NW, RPL>(), 3>(dc, ra, order, st);
 #endif
-    return launch_rollout<NW, RPL, OBS, 32, AGV_ROLL_NB, 0>(dc, ra, order, st);
+    return launch_rollout<NW, RPL, OBS, 32, rollout_nb<NW, RPL>(), 0>(dc, ra, order, st);
 }
 
 template <int NW, int RPL>

@@ -33,6 +33,9 @@ constexpr int ROLL_RING = 32;  // tick-end record requests in flight per scene w
 #ifndef AGV_ROLL_WORKER_NS
 #define AGV_ROLL_WORKER_NS 1000
 #endif
+#ifndef AGV_ROLL_WORKER_FAST_NS
+#define AGV_ROLL_WORKER_FAST_NS 250
+#endif
 #ifndef AGV_ROLL_WRITER_NS
 #define AGV_ROLL_WRITER_NS 4000
 #endif
@@ -79,7 +82,7 @@ struct RollShared {
     int exit_flag;
     unsigned done_warps;
     unsigned done_slots;      // slots that found the scene queue empty
-    int pad;
+    unsigned heavy_live;      // scenes the heavy warp is running: the workers poll faster while there are any
     unsigned enc_head[2], enc_tail[2];
     uint4 enc_ring[2][ROLL_RING];          // {first record of the scene-tick, acted lo, acted hi, -}
     unsigned long long recbits[64][3];     // writer staging: the 147-bit strings of one scene-tick's records
@@ -250,7 +253,8 @@ __device__ __forceinline__ void roll_worker(const DevCfg &c, const RollArgs &ra,
         unsigned m = __ballot_sync(FULL, s == 1u || s == 4u);
         if (!m) {
             if (*vexit) return;
-            __nanosleep(AGV_ROLL_WORKER_NS);
+            // BFS round trips are the critical path of the heavy scenes only: quick wake-ups while the CTA has any
+            __nanosleep(*reinterpret_cast<volatile unsigned *>(&sh->heavy_live) ? AGV_ROLL_WORKER_FAST_NS : AGV_ROLL_WORKER_NS);
             continue;
         }
         int j = -1;
@@ -476,6 +480,10 @@ __device__ __forceinline__ void roll_scene_warp(const DevCfg &c, const RollArgs 
                 else __nanosleep(AGV_ROLL_IDLE_NS);
                 RQ(0)
                 continue;
+            }
+            if (which == 1) {
+                const unsigned live = __ballot_sync(FULL, st != LS_IDLE);
+                if (lane == 0) *reinterpret_cast<volatile unsigned *>(&sh->heavy_live) = live;
             }
             // ---- slots handed to this warp (freshly loaded by a worker, or migrated from the other scene warp)
             if (pick) {
@@ -734,7 +742,7 @@ __device__ __forceinline__ void rollout_cta(const DevCfg &c, const RollArgs &ra,
     if (warp == 0) {
         sh->bfs_state[lane] = 0u; sh->ctl[lane] = 4u; sh->slot_e[lane] = -1; sh->slot_k[lane] = 0; sh->slot_fl[lane] = 0u;
         if (lane == 0) {
-            sh->exit_flag = 0; sh->done_warps = 0u; sh->done_slots = 0u;
+            sh->exit_flag = 0; sh->done_warps = 0u; sh->done_slots = 0u; sh->heavy_live = 0u;
             sh->enc_head[0] = sh->enc_head[1] = 0u; sh->enc_tail[0] = sh->enc_tail[1] = 0u;
         }
     } else if (warp == 1) {
