@@ -140,15 +140,18 @@ int agv_tick_host_join(AgvHandle *h, void *stream);
  * This is Scene.run_game("A_star") / Expert.create_data_by_self (ExpertManager.py:35-52) and the
  * A*-guided branch of AG-DQN (MADQN.py:96-111 with u >= epsilon) for E scenes at once: no network is
  * in the loop, so a scene never has to wait for the other scenes between its ticks.  Scenes are
- * scheduled heaviest-first (by the BFS count of their last tick) onto persistent CTAs.  Inside a
- * written group of 8 observation records, records of AGVs without a turn are zero-filled; mask with
- * act_out >= 0 as for agv_tick.  Configurations the persistent kernel does not cover (shaped reward,
- * full-map observations, K != 7) run as n_ticks fused ticks -- same results. */
+ * scheduled longest-first (by the turns + BFS searches of their last tick) onto persistent CTAs; long
+ * rollouts are taken 16 ticks per launch.  Inside a written group of 8 observation records, records of AGVs
+ * without a turn are zero-filled; mask with act_out >= 0 as for agv_tick.  Configurations the persistent
+ * kernel does not cover (shaped reward, full-map observations, K != 7) and maps up to 32 rows x 64 columns
+ * (where the warp-per-scene tick is faster) run as n_ticks fused ticks inside this call -- same results. */
 int agv_rollout(AgvHandle *h, int32_t n_ticks, int32_t proto, int32_t policy, int32_t obs_kind,
                 const int8_t *action_dev, int8_t *act_out_dev, float *reward_dev, uint8_t *done_dev,
                 uint16_t *plen_dev, uint16_t *slen_dev, void *obs_dev, void *next_obs_dev, void *stream);
 /* Same with HOST (pinned) buffers for the [n_ticks,E,N] actions in and act / reward / done out;
- * double-buffered and overlapped like agv_tick_host; agv_tick_host_join waits for the copy-backs. */
+ * double-buffered and overlapped like agv_tick_host, and pipelined inside the call: the rollout runs in
+ * chunks of 4 ticks whose actions are uploaded and whose results are copied back while the neighbouring
+ * chunks compute.  agv_tick_host_join waits for the copy-backs. */
 int agv_rollout_host(AgvHandle *h, int32_t n_ticks, int32_t proto, int32_t policy, int32_t obs_kind,
                      const int8_t *action_host, int8_t *act_out_host, float *reward_host, uint8_t *done_host,
                      void *obs_dev, void *next_obs_dev, void *stream);

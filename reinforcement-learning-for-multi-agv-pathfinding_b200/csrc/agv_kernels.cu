@@ -356,7 +356,7 @@ struct AgvHandle {
     bool copy_pending[2] = {false, false};
     unsigned host_calls = 0;
     std::vector<uint8_t> h_state;
-    // persistent rollout (agv_rollout): heaviest-first scene order + queue counter, packed-window scratch
+    // persistent rollout (agv_rollout): longest-first scene order + queue counter, packed-window scratch
     // rings of the record writer, and double-buffered result rings for agv_rollout_host
     unsigned *d_order = nullptr, *d_qctr = nullptr;
     unsigned long long *d_scr[2] = {nullptr, nullptr};
@@ -528,7 +528,7 @@ static int rollout_launch(AgvHandle *h, int n_ticks, int proto, int policy, int 
     if (plen_dev) CUDA_TRY(cudaMemsetAsync(plen_dev, 0, n * sizeof(uint16_t), st));
     if (slen_dev) CUDA_TRY(cudaMemsetAsync(slen_dev, 0xFF, n * sizeof(uint16_t), st));
     const int rc = lanes_rollout(d, h->NW, h->RPL, ra, h->d_order, st);
-    if (rc == 0) g_tick_kernel = "k_rollout (persistent lane-per-scene rollout, heaviest-first scene queue)";
+    if (rc == 0) g_tick_kernel = "k_rollout (persistent lane-per-scene rollout, longest-first scene queue)";
     return rc;
 }
 

@@ -7,7 +7,7 @@
 // tick counter next to its own turn cursor, same decoupled-lane state machine as agv_async.cuh),
 // outputs go to [n_ticks, E, N, ...] rings, and CTAs are persistent: when a scene has finished its
 // n_ticks the slot is handed to a BFS worker warp, which writes the scene block back, takes the next
-// scene from a global queue (heaviest first -- ordered by the BFS count of the scene's last tick)
+// scene from a global queue (longest first -- ordered by the turns + BFS searches of the scene's last tick)
 // and loads it.  Long scenes start first and short ones fill in behind them.
 //
 // Warp roles in a CTA:  warps 0..NB-1    BFS workers: level-synchronous BFS requests + slot swaps
@@ -16,8 +16,7 @@
 //                                        the packed 49-bit windows into [3,7,7] bf16 records with
 //                                        16-byte stores (8 records = 147 uint4, always aligned)
 //                       warps NB+1 / +2  scene warps: the slots whose last tick was heavy / light
-//                                        (a slot migrates between them at tick boundaries); highest
-//                                        warp ids = first pick of the issue arbiter
+//                                        (a slot migrates between them at tick boundaries)
 // Results are bit-identical to n_ticks calls of agv_tick (tests/test_gpu_rollout.py).
 #pragma once
 #include "agv_async.cuh"
@@ -55,7 +54,7 @@ struct RollArgs {
     // (wm = 49-bit window of matrix (b) before the move), scr_next [K*E*N] wm | tpos << 49 after the move
     ulonglong2 *scr_turn;
     unsigned long long *scr_next;
-    const unsigned *order;    // [E] scene indices, heaviest first
+    const unsigned *order;    // [E] scene indices, longest first
     unsigned *qctr;           // next entry of `order` to hand out
     unsigned long long *prof; // -DAGV_ROLL_PROF builds: [E][8] per-scene timeline (agv_rollout_profile)
 };
@@ -750,7 +749,7 @@ __device__ __forceinline__ void rollout_cta(const DevCfg &c, const RollArgs &ra,
         ws.load_tables();
     }
     __syncthreads();
-    // first fill: slot j of CTA b takes entry b + j * gridDim of the heaviest-first order, so the heavy
+    // first fill: slot j of CTA b takes entry b + j * gridDim of the longest-first order, so the long
     // scenes are spread over all CTAs; later scenes come from the queue counter (starts at SPW * gridDim)
     for (int j = warp; j < SPW; j += n_warps) {
         const unsigned idx = blockIdx.x + (unsigned)j * gridDim.x;
@@ -758,11 +757,10 @@ __device__ __forceinline__ void rollout_cta(const DevCfg &c, const RollArgs &ra,
         else if (lane == 0) atomicAdd(&sh->done_slots, 1u);
     }
     __syncthreads();
-    // Role by warp index.  The SM sub-partition's arbiter picks the eligible warp with the HIGHEST warp id
-    // first: the scene warps, whose dependent instruction chains are the critical path of every scene, get
-    // the highest ids of the CTA, the BFS workers and the record writer (throughput work with slack) the
-    // lowest.  (With the scene warps at ids 0 / 1 every instruction of theirs waited for the workers' BFS
-    // loops on the same sub-partition: ~5.7 cycles per instruction in the row-DP loop.)
+    // Role by warp index.  The SM sub-partition's arbiter is reported to pick the eligible warp with the highest
+    // warp id first, so the scene warps -- whose dependent instruction chains are the critical path of every
+    // scene -- get the highest ids of the CTA, the BFS workers and the record writer (throughput work with
+    // slack) the lowest.  (Measured against scene warps at ids 0 / 1: no difference, 1.06e9 both ways.)
     if (warp < NB) roll_worker<NW, RPL, SPW>(c, ra, smem);
     else if (warp == NB) roll_writer(ra, smem);  // (also without observations: it unpacks act / reward / done / plen)
     else roll_scene_warp<NW, RPL, OBS, SPW, MODE>(c, ra, smem, warp == NB + 2 ? 0 : 1);

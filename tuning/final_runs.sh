@@ -12,3 +12,15 @@ python bench.py --workload c2 --ticks 32 --no-sub > $o/r02_bench_c2.json 2>/dev/
 python bench.py --workload c5 --ticks 8 --steps 10 --no-sub > $o/r02_bench_c5.json 2>/dev/null
 python bench.py --mode substep --no-cpu-baseline > $o/r02_bench_c3_substep.json 2>/dev/null
 for f in $o/r02_bench_*.json; do echo "== $f"; python tuning/brief.py < $f 2>/dev/null || tail -c 300 $f; done
+# refresh of the headline kernel's ncu capture + launch list
+run() {
+  name=$1; re=$2; skip=$3; cnt=$4; shift 4
+  "$@" > $o/ncu_plain_$name.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k "regex:$re" -s $skip -c $cnt -f -o $o/r02_$name "$@" > $o/ncu_$name.log 2>&1
+  ncu -i $o/r02_$name.ncu-rep --page raw --csv > $o/r02_$name.raw.csv 2>/dev/null
+}
+run c3 '^k_rollout$' 30 1 python bench.py --steps 3 --warmup 3 --reps 1 --no-cpu-baseline --no-sub
+run c5 '^k_rollout$' 52 1 python bench.py --workload c5 --steps 3 --warmup 3 --reps 1 --ticks 8 --no-cpu-baseline --no-sub
+rm -f $o/r02_c5.ncu-rep
+python bench.py --steps 4 --warmup 3 --reps 1 --no-cpu-baseline --no-sub > $o/launch_plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 120 --csv --log-file $o/r02_launches_c3.csv python bench.py --steps 4 --warmup 3 --reps 1 --no-cpu-baseline --no-sub > $o/launch_ncu.log 2>&1
