@@ -665,7 +665,10 @@ def main():
     sm_mhz = (clk or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
     n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
     issue = None
-    if prof.get("warp_instr_per_agv_step"):
+    # (the committed profile is of the headline configuration only: guided policy, clip obs, sparse reward, the
+    # profile's ticks per launch -- other configurations run other kernels / instruction mixes)
+    if (prof.get("warp_instr_per_agv_step") and prof.get("ticks_per_launch") == KK and guided and args.obs == "clip"
+            and not args.shaped):
         # binding roof of the limited-visual rollout: instruction issue of the scene warps' dependent chains.
         # achieved = warp instructions per launch (ncu smsp__inst_executed.sum per AGV-step of the committed
         # profile x the AGV-steps of this launch) / launch duration; peak = 1 warp instruction per cycle and SM

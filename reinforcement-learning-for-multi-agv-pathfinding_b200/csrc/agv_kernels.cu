@@ -359,6 +359,7 @@ struct AgvHandle {
     // persistent rollout (agv_rollout): longest-first scene order + queue counter, packed-window scratch
     // rings of the record writer, and double-buffered result rings for agv_rollout_host
     unsigned *d_order = nullptr, *d_qctr = nullptr;
+    unsigned long long *h_rstat = nullptr;  // pinned: load figure written by k_rollout_order (agv_rollout.cu)
     unsigned long long *d_scr[2] = {nullptr, nullptr};
     size_t scr_cap[2] = {0, 0};
     int8_t *r_action[2] = {nullptr, nullptr}, *r_act_out[2] = {nullptr, nullptr};
@@ -495,6 +496,8 @@ static int rollout_launch(AgvHandle *h, int n_ticks, int proto, int policy, int 
     if (!h->d_order) {
         CUDA_TRY(cudaMalloc(&h->d_order, sizeof(unsigned) * (size_t)d.E));
         CUDA_TRY(cudaMalloc(&h->d_qctr, sizeof(unsigned)));
+        CUDA_TRY(cudaHostAlloc(&h->h_rstat, 2 * sizeof(unsigned long long), cudaHostAllocMapped));
+        h->h_rstat[0] = h->h_rstat[1] = 0ull;
     }
     // per-turn scratch records of the scene lanes (agv_rollout.cuh): 16 B per turn, + 8 B with next_obs
     const size_t need[2] = {n * 2, next_obs_dev ? n : 0};
@@ -513,6 +516,7 @@ static int rollout_launch(AgvHandle *h, int n_ticks, int proto, int policy, int 
     ra.K = n_ticks;
     ra.scr_turn = reinterpret_cast<ulonglong2 *>(h->d_scr[0]); ra.scr_next = h->d_scr[1];
     ra.qctr = h->d_qctr;
+    ra.stat = h->h_rstat;  // (unified addressing: the pinned host pointer is valid on the device)
 #ifdef AGV_ROLL_PROF
     if (getenv("AGV_ROLL_PROF")) {
         if (!h->d_prof) CUDA_TRY(cudaMalloc(&h->d_prof, sizeof(unsigned long long) * 8 * (size_t)d.E));
@@ -605,6 +609,7 @@ int agv_destroy(AgvHandle *h) {
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
     cudaFree(h->d_order); cudaFree(h->d_qctr); cudaFree(h->d_prof);
+    if (h->h_rstat) cudaFreeHost(h->h_rstat);
     for (int b = 0; b < 2; b++) {
         cudaFree(h->d_scr[b]);
         cudaFree(h->r_action[b]); cudaFree(h->r_act_out[b]); cudaFree(h->r_reward[b]); cudaFree(h->r_done[b]);

@@ -2,6 +2,7 @@
 // sm_100a only.  Called from agv_rollout / agv_tick (agv_kernels.cu).
 #include "agv_rollout.cuh"
 
+#include <cstdio>
 #include <cstdlib>
 
 namespace agv {
@@ -26,19 +27,30 @@ __device__ __forceinline__ unsigned order_bucket(unsigned w) {
     return 63u - min(((w & 0xFFFFu) + (w >> 16)) >> 1, 63u);
 }
 
-__global__ void __launch_bounds__(1024) k_rollout_order(const DevCfg c, unsigned *order, unsigned *qctr, unsigned q0) {
+__global__ void __launch_bounds__(1024) k_rollout_order(const DevCfg c, unsigned *order, unsigned *qctr, unsigned q0,
+                                                        unsigned long long *stat) {
     __shared__ unsigned hist[64], base[64];
+    __shared__ unsigned long long load[2];
     if (threadIdx.x < 64) hist[threadIdx.x] = 0u;
+    if (threadIdx.x < 2) load[threadIdx.x] = 0ull;
     __syncthreads();
+    unsigned n_bfs = 0, n_turns = 0;
     for (int e = threadIdx.x; e < c.E; e += blockDim.x) {
         const unsigned w = *reinterpret_cast<const unsigned *>(c.state + (size_t)e * c.env_stride + 24);
         atomicAdd(&hist[order_bucket(w)], 1u);
+        n_bfs += w & 0xFFFFu; n_turns += w >> 16;
     }
+    n_bfs = __reduce_add_sync(FULL, n_bfs); n_turns = __reduce_add_sync(FULL, n_turns);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&load[0], (unsigned long long)n_bfs); atomicAdd(&load[1], (unsigned long long)n_turns); }
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned s = 0;
         for (int b = 0; b < 64; b++) { base[b] = s; s += hist[b]; }
         *qctr = q0;
+        if (stat) {  // read by the host before the next launch, without synchronisation: a hint, never a result
+            reinterpret_cast<volatile unsigned long long *>(stat)[0] = load[0];
+            reinterpret_cast<volatile unsigned long long *>(stat)[1] = load[1];
+        }
     }
     __syncthreads();
     for (int e = threadIdx.x; e < c.E; e += blockDim.x) {
@@ -71,7 +83,7 @@ static int env_int(const char *name, int dflt) {
 }
 
 template <int NW, int RPL, int OBS, int SPW, int NB, int MODE>
-static int launch_rollout(const DevCfg &dc, RollArgs ra, unsigned *order, cudaStream_t st) {
+static int launch_rollout(const DevCfg &dc, RollArgs ra, unsigned *order, cudaStream_t st, int cps_want = 0) {
     const int smem = plan_rollout<NW, SPW>(dc, ra.la);
     auto kern = k_rollout<NW, RPL, OBS, SPW, NB, MODE>;
     const int threads = 32 * (3 + NB);  // 2 scene warps, NB BFS workers, the record writer
@@ -95,11 +107,11 @@ static int launch_rollout(const DevCfg &dc, RollArgs ra, unsigned *order, cudaSt
     // or more: co-resident CTAs slow each other's dependent turn chains more than the scene queue costs
     // (c3, 16384 scenes on 148 SMs: 4 per SM = all scenes resident, 1.10e9 AGV-steps/s; 3 per SM = 13 % of the
     // scenes -- the shortest ones -- wait in the queue, 1.15e9; 2 per SM 0.97e9).  AGV_ROLLOUT_CPS overrides.
-    int cps = env_int("AGV_ROLLOUT_CPS", 0);
+    int cps = env_int("AGV_ROLLOUT_CPS", cps_want);
     if (cps < 1 || cps > cps_cached) cps = cps_cached >= 3 ? cps_cached - 1 : cps_cached;
     int ctas = (dc.E + SPW - 1) / SPW;
     if (ctas > sms * cps) ctas = sms * cps;
-    k_rollout_order<<<1, 1024, 0, st>>>(dc, order, ra.qctr, (unsigned)ctas * SPW);
+    k_rollout_order<<<1, 1024, 0, st>>>(dc, order, ra.qctr, (unsigned)ctas * SPW, ra.stat);
     note_launch();
     ra.order = order;
     kern<<<ctas, threads, smem, st>>>(dc, ra);
@@ -112,27 +124,59 @@ static int launch_rollout(const DevCfg &dc, RollArgs ra, unsigned *order, cudaSt
 // protocol / policy specialisations (agv_rollout.cuh, MODE): the two modes the rollout exists for get their
 // own kernels; open-loop actions and mixed settings run on the generic one
 // BFS worker warps per CTA.  64 x 64 (c3, 16 ticks): 2 -> 1.10e9, 3 -> 1.06e9, 4 -> 0.99e9 AGV-steps/s (the scene warps'
-// turn chains bind, more workers only compete for issue slots).  128 x 128 (c5, 8 ticks): searches are 4x longer
-// (4 rows x 2 words per lane, paths up to ~250 levels) and bind: 2 -> 2.08e8, 3 -> 2.31e8, 4 -> 2.44e8 (A_star
-// control mode 1.42e8 -> 1.89e8); 5 would not leave registers for 2 CTAs per SM.  AGV_ROLL_NB overrides (tuning).
+// turn chains bind, more workers only compete for issue slots).  AGV_ROLL_NB overrides (tuning builds).
+//
+// 128-column maps (c5; 4 rows x 2 words per lane, 144 registers, 91 KB of shared memory per CTA) have two shapes:
+//   "light": 3 workers, 2 CTAs per SM -- few searches, the scene warps' row DP binds (128 rows!), four scene
+//            warps per SM do twice the work of two;
+//   "heavy": 5 workers, 1 CTA per SM (8 warps x 144 registers do not fit twice) -- congested scenes, the
+//            searches (~100 levels x 4 rows x 2 words) bind and a second CTA only slows them.
+// Measured, AGV-steps/s (light / heavy shape): Expert collection 128 ticks after Scene.init, 4 searches per 100
+// turns: 3.49e8 / 2.17e8; stationary guided rollout, 11 per 100: 2.29e8 / 2.46e8; stationary A_star control mode,
+// 22 per 100: 1.61e8 / 1.91e8.  The launch picks by the load of every scene's last tick (searches per 100 turns, summed by the previous
+// launch's order kernel into pinned host memory -- a hint that never changes a result).
+#ifndef AGV_ROLL_HEAVY_PCT
+#define AGV_ROLL_HEAVY_PCT 8
+#endif
 template <int NW, int RPL>
 constexpr int rollout_nb() {
 #ifdef AGV_ROLL_NB
     return AGV_ROLL_NB;
 #else
-    return NW * RPL <= 2 ? 2 : (NW * RPL <= 4 ? 3 : 4);
+    return NW * RPL <= 2 ? 2 : 3;
 #endif
+}
+
+template <int NW, int RPL, int OBS, int MODE>
+static int launch_shape(const DevCfg &dc, const RollArgs &ra, unsigned *order, cudaStream_t st) {
+#ifndef AGV_ROLL_NB
+    if (NW * RPL > 4) {
+        const int shape_env = env_int("AGV_ROLLOUT_SHAPE", 0);  // 1 = light, 2 = heavy (tests, tuning)
+        static bool heavy = false;  // (kept while the figure is unknown: right after agv_set_state / agv_reset)
+        if (ra.stat && reinterpret_cast<volatile unsigned long long *>(ra.stat)[1] > 0) {
+            const unsigned long long n_bfs = reinterpret_cast<volatile unsigned long long *>(ra.stat)[0],
+                                     n_turns = reinterpret_cast<volatile unsigned long long *>(ra.stat)[1];
+            heavy = n_bfs * 100ull >= n_turns * (unsigned long long)AGV_ROLL_HEAVY_PCT;
+            static const bool dump = getenv("AGV_PROF_DUMP") != nullptr;
+            if (dump) fprintf(stderr, "agv rollout load: %llu searches / %llu turns in the scenes' last ticks -> %s\n", n_bfs, n_turns, heavy ? "heavy" : "light");
+        }
+        const bool hv = shape_env ? shape_env == 2 : heavy;
+        if (hv) return launch_rollout<NW, RPL, OBS, 32, (NW * RPL > 4 ? 5 : 3), MODE>(dc, ra, order, st, 1);
+        return launch_rollout<NW, RPL, OBS, 32, 3, MODE>(dc, ra, order, st, 2);
+    }
+#endif
+    return launch_rollout<NW, RPL, OBS, 32, rollout_nb<NW, RPL>(), MODE>(dc, ra, order, st);
 }
 
 template <int NW, int RPL, int OBS>
 static int dispatch_mode(const DevCfg &dc, const RollArgs &ra, unsigned *order, cudaStream_t st) {
     const LaneArgs &t = ra.la;
 #ifndef AGV_ROLL_GENERIC_ONLY
-    if (t.proto == PROTO_INTELLIGENT && t.policy == POLICY_GUIDED) return launch_rollout<NW, RPL, OBS, 32, rollout_nb<NW, RPL>(), 1>(dc, ra, order, st);
-    if (t.proto == PROTO_ASTAR && t.policy == POLICY_ASTAR) return launch_rollout<NW, RPL, OBS, 32, rollout_nb<NW, RPL>(), 2>(dc, ra, order, st);
-    if (t.proto == PROTO_INTELLIGENT && t.policy == POLICY_GIVEN) return launch_rollout<NW, RPL, OBS, 32, rollout_nb<NW, RPL>(), 3>(dc, ra, order, st);
+    if (t.proto == PROTO_INTELLIGENT && t.policy == POLICY_GUIDED) return launch_shape<NW, RPL, OBS, 1>(dc, ra, order, st);
+    if (t.proto == PROTO_ASTAR && t.policy == POLICY_ASTAR) return launch_shape<NW, RPL, OBS, 2>(dc, ra, order, st);
+    if (t.proto == PROTO_INTELLIGENT && t.policy == POLICY_GIVEN) return launch_shape<NW, RPL, OBS, 3>(dc, ra, order, st);
 #endif
-    return launch_rollout<NW, RPL, OBS, 32, rollout_nb<NW, RPL>(), 0>(dc, ra, order, st);
+    return launch_shape<NW, RPL, OBS, 0>(dc, ra, order, st);
 }
 
 template <int NW, int RPL>

@@ -56,6 +56,8 @@ struct RollArgs {
     unsigned long long *scr_next;
     const unsigned *order;    // [E] scene indices, longest first
     unsigned *qctr;           // next entry of `order` to hand out
+    unsigned long long *stat; // pinned host memory, written by the order kernel: {BFS searches, turns} of every
+                              // scene's last tick -- the load figure the NEXT launch picks its shape by
     unsigned long long *prof; // -DAGV_ROLL_PROF builds: [E][8] per-scene timeline (agv_rollout_profile)
 };
 
@@ -683,6 +685,9 @@ __device__ __forceinline__ void roll_scene_warp(const DevCfg &c, const RollArgs 
             int l = 0;
             RPROF(rows_ += __reduce_max_sync(FULL, need ? abs(ty - sy) : 0);)
             RQ(6)
+            // (Remembering per AGV that its last search needed the BFS, and skipping the row DP for it next time,
+            // was measured: -5 % at c3, -5 % in A_star mode -- the jams are too short-lived, and every stale bit
+            // turns a 2k-cycle DP into a 10k-cycle BFS round trip.)
             const int ma = lane_monotone_pf<NW>(need, ws.tab, ws.HN, om ? ws.occ : zr, om ? ws.occm : zr, a.loaded, sx, sy,
                                                 tx, ty, l);
             RQ(7)

@@ -233,3 +233,22 @@ def test_two_rank_gradient_mean_equals_single_rank_gradient():
     for p in ps:
         p.join(timeout=120)
     assert err < 1e-5, err
+
+
+def test_bench_reference_arm_line():
+    """`bench.py --impl reference` (the driver's second arm) runs without a GPU: the unmodified Python
+    reference from baseline/_ref (or /root/reference) when present, else the oracle C port, and prints one
+    JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "3",
+                          "--ref-seconds", "0.5", "--workload", "c2"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "AGV-steps/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["e2e"]["value"] == line["value"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["config"]["agvs_per_scene"] == 4 and line["config"]["scenes_per_gpu"] == 4096

@@ -7,21 +7,24 @@ import bench
 pkg = importlib.import_module(bench.PKG)
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 wl = sys.argv[2] if len(sys.argv) > 2 else "c3"
+mode = sys.argv[3] if len(sys.argv) > 3 else "guided"   # "expert": A_star control mode + next_obs (collect_expert's rollout)
+PROTO, POL, NEXT = ((pkg.PROTO_ASTAR, pkg.POLICY_ASTAR, True) if mode == "expert" else
+                    (pkg.PROTO_INTELLIGENT, pkg.POLICY_GUIDED, False))
 gridf, N, E, _ = bench.WORKLOADS[wl]
 grid = gridf()
 sc = pkg.BatchedScene(grid, E, N, tasks=bench.synth_tasks(grid, E, 1000), auto_reset=True)
 sc.reset()
 out = {}
 for _ in range(2 * N // 16 + 1):
-    sc.rollout(16, pkg.PROTO_INTELLIGENT, pkg.POLICY_GUIDED, pkg.OBS_CLIP, want_lens=False, out=out)
+    sc.rollout(16, PROTO, POL, pkg.OBS_CLIP, want_next=NEXT, want_lens=False, out=out)
 out = {}
 for _ in range(2):
-    sc.rollout(K, pkg.PROTO_INTELLIGENT, pkg.POLICY_GUIDED, pkg.OBS_CLIP, want_lens=False, out=out)
+    sc.rollout(K, PROTO, POL, pkg.OBS_CLIP, want_next=NEXT, want_lens=False, out=out)
 for rep in range(2):
     sc.counters()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    sc.rollout(K, pkg.PROTO_INTELLIGENT, pkg.POLICY_GUIDED, pkg.OBS_CLIP, want_lens=False, out=out)
+    sc.rollout(K, PROTO, POL, pkg.OBS_CLIP, want_next=NEXT, want_lens=False, out=out)
     ev1.record(); torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
     if rep == 1:
