@@ -122,50 +122,53 @@ static int launch_rollout(const DevCfg &dc, RollArgs ra, unsigned *order, cudaSt
 }
 
 // protocol / policy specialisations (agv_rollout.cuh, MODE): the two modes the rollout exists for get their
-// own kernels; open-loop actions and mixed settings run on the generic one
-// BFS worker warps per CTA.  64 x 64 (c3, 16 ticks): 2 -> 1.10e9, 3 -> 1.06e9, 4 -> 0.99e9 AGV-steps/s (the scene warps'
-// turn chains bind, more workers only compete for issue slots).  AGV_ROLL_NB overrides (tuning builds).
+// own kernels; open-loop actions and mixed settings run on the generic one.
 //
-// 128-column maps (c5; 4 rows x 2 words per lane, 144 registers, 91 KB of shared memory per CTA) have two shapes:
-//   "light": 3 workers, 2 CTAs per SM -- few searches, the scene warps' row DP binds (128 rows!), four scene
-//            warps per SM do twice the work of two;
-//   "heavy": 5 workers, 1 CTA per SM (8 warps x 144 registers do not fit twice) -- congested scenes, the
-//            searches (~100 levels x 4 rows x 2 words) bind and a second CTA only slows them.
-// Measured, AGV-steps/s (light / heavy shape): Expert collection 128 ticks after Scene.init, 4 searches per 100
-// turns: 3.49e8 / 2.17e8; stationary guided rollout, 11 per 100: 2.29e8 / 2.46e8; stationary A_star control mode,
-// 22 per 100: 1.61e8 / 1.91e8.  The launch picks by the load of every scene's last tick (searches per 100 turns, summed by the previous
-// launch's order kernel into pinned host memory -- a hint that never changes a result).
-#ifndef AGV_ROLL_HEAVY_PCT
-#define AGV_ROLL_HEAVY_PCT 8
-#endif
+// Launch shape = BFS worker warps per CTA x CTAs per SM.  The best shape depends on how many turns need the
+// level-synchronous BFS (the row DP decides the others inside the scene warp): with few searches the scene
+// warps' turn chains bind and idle workers only compete for issue slots; with many, the searches bind.  Two
+// shapes per map class, picked per launch by the load of every scene's last tick -- searches per 100 turns,
+// summed by the previous launch's order kernel into pinned host memory (a hint: the schedule never changes a
+// result).  Measured, AGV-steps/s (light / heavy shape):
+//   64 x 64 (c3, 16 ticks), light = 2 workers x 3 CTAs, heavy = 6 x 3:
+//       guided rollout (7 searches per 100 turns)        1.18e9 / 0.91e9     (4 x 3: 1.16e9, 3 x 3: 1.13e9)
+//       A_star control mode (all AGVs act, congested)    4.41e8 / 6.06e8     (4 x 3: 5.7e8, 6 x 2: 6.0e8, 8 x 3: 5.7e8)
+//   128 x 128 (c5, 8 ticks; 4 rows x 2 words per lane, 144 registers, 91 KB shared memory per CTA),
+//   light = 3 x 2, heavy = 5 x 1 (8 warps x 144 registers do not fit twice):
+//       Expert collection 128 ticks after Scene.init (4 per 100)   3.49e8 / 2.17e8
+//       stationary guided rollout (11 per 100)                      2.29e8 / 2.46e8
+//       stationary A_star control mode (22 per 100)                 1.61e8 / 1.91e8
+// Map classes in between (64 x 128, 128 x 64) run 3 workers; AGV_ROLL_NB fixes the worker count (tuning builds),
+// AGV_ROLLOUT_SHAPE=1|2 forces light | heavy (tests), AGV_ROLLOUT_CPS the CTAs per SM.
 template <int NW, int RPL>
-constexpr int rollout_nb() {
-#ifdef AGV_ROLL_NB
-    return AGV_ROLL_NB;
-#else
-    return NW * RPL <= 2 ? 2 : 3;
-#endif
-}
+struct RollShape {
+    static constexpr bool two = NW * RPL <= 2 || NW * RPL > 4;
+    static constexpr int nb_light = NW * RPL <= 2 ? 2 : 3, cps_light = NW * RPL > 4 ? 2 : 0;   // cps 0: occupancy - 1
+    static constexpr int nb_heavy = NW * RPL <= 2 ? 6 : (NW * RPL > 4 ? 5 : 3), cps_heavy = NW * RPL > 4 ? 1 : 0;
+    static constexpr int heavy_pct = NW * RPL <= 2 ? 15 : 8;   // searches per 100 turns from which the heavy shape runs
+};
 
 template <int NW, int RPL, int OBS, int MODE>
 static int launch_shape(const DevCfg &dc, const RollArgs &ra, unsigned *order, cudaStream_t st) {
-#ifndef AGV_ROLL_NB
-    if (NW * RPL > 4) {
-        const int shape_env = env_int("AGV_ROLLOUT_SHAPE", 0);  // 1 = light, 2 = heavy (tests, tuning)
+#ifdef AGV_ROLL_NB
+    return launch_rollout<NW, RPL, OBS, 32, AGV_ROLL_NB, MODE>(dc, ra, order, st);
+#else
+    using S = RollShape<NW, RPL>;
+    if (S::two) {
         static bool heavy = false;  // (kept while the figure is unknown: right after agv_set_state / agv_reset)
         if (ra.stat && reinterpret_cast<volatile unsigned long long *>(ra.stat)[1] > 0) {
             const unsigned long long n_bfs = reinterpret_cast<volatile unsigned long long *>(ra.stat)[0],
                                      n_turns = reinterpret_cast<volatile unsigned long long *>(ra.stat)[1];
-            heavy = n_bfs * 100ull >= n_turns * (unsigned long long)AGV_ROLL_HEAVY_PCT;
+            heavy = n_bfs * 100ull >= n_turns * (unsigned long long)S::heavy_pct;
             static const bool dump = getenv("AGV_PROF_DUMP") != nullptr;
             if (dump) fprintf(stderr, "agv rollout load: %llu searches / %llu turns in the scenes' last ticks -> %s\n", n_bfs, n_turns, heavy ? "heavy" : "light");
         }
-        const bool hv = shape_env ? shape_env == 2 : heavy;
-        if (hv) return launch_rollout<NW, RPL, OBS, 32, (NW * RPL > 4 ? 5 : 3), MODE>(dc, ra, order, st, 1);
-        return launch_rollout<NW, RPL, OBS, 32, 3, MODE>(dc, ra, order, st, 2);
+        const int shape_env = env_int("AGV_ROLLOUT_SHAPE", 0);
+        if (shape_env ? shape_env == 2 : heavy)
+            return launch_rollout<NW, RPL, OBS, 32, S::nb_heavy, MODE>(dc, ra, order, st, S::cps_heavy);
     }
+    return launch_rollout<NW, RPL, OBS, 32, S::nb_light, MODE>(dc, ra, order, st, S::cps_light);
 #endif
-    return launch_rollout<NW, RPL, OBS, 32, rollout_nb<NW, RPL>(), MODE>(dc, ra, order, st);
 }
 
 template <int NW, int RPL, int OBS>

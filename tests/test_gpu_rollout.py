@@ -102,13 +102,14 @@ def test_rollout_equals_single_ticks(pkg, case):
     assert turns > K * rounds
 
 
-@pytest.mark.parametrize("shape", [1, 2], ids=["light_3workers_2ctas", "heavy_5workers_1cta"])
+@pytest.mark.parametrize("shape", [1, 2], ids=["light", "heavy"])
 @pytest.mark.parametrize("proto,policy", [(1, 2), (0, 1)], ids=["guided", "astar_mode"])
-def test_rollout_128_columns_both_launch_shapes(pkg, monkeypatch, shape, proto, policy):
-    """maps wider than 64 columns have two launch shapes of the persistent kernel, picked by a load hint
-    (agv_rollout.cu: launch_shape); either must reproduce the single ticks bit-exactly"""
+@pytest.mark.parametrize("layout", [(6, 2, 18, 41, 9), (6, 2, 9, 20, 8)], ids=["127x127", "64x64"])
+def test_rollout_both_launch_shapes(pkg, monkeypatch, layout, shape, proto, policy):
+    """the persistent kernel has two launch shapes per map class (BFS workers per CTA x CTAs per SM), picked by
+    a load hint (agv_rollout.cu: launch_shape); either must reproduce the single ticks bit-exactly"""
     monkeypatch.setenv("AGV_ROLLOUT_SHAPE", str(shape))
-    grid = orc.rect_layout(6, 2, 18, 41, 9)  # 127 x 127
+    grid = orc.rect_layout(*layout)
     E, N, K = 40, 48, 6
     tasks = np.array([orc.make_tasks(grid, random.Random(300 + e)) for e in range(E)], dtype=np.uint8)
     turns = _compare_rollout_with_ticks(pkg, grid, E, N, tasks, K, 6, proto, policy, pkg.OBS_CLIP, True, seed=9)
