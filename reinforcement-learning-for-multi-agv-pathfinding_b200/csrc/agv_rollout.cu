@@ -140,10 +140,13 @@ static int launch_rollout(const DevCfg &dc, RollArgs ra, unsigned *order, cudaSt
 //       stationary A_star control mode (22 per 100)                 1.61e8 / 1.91e8
 // Map classes in between (64 x 128, 128 x 64) run 3 workers; AGV_ROLL_NB fixes the worker count (tuning builds),
 // AGV_ROLLOUT_SHAPE=1|2 forces light | heavy (tests), AGV_ROLLOUT_CPS the CTAs per SM.
+#ifndef AGV_ROLL_SPW
+#define AGV_ROLL_SPW 32   // scene slots per CTA = lanes of a scene warp in use (tuning builds: 16)
+#endif
 template <int NW, int RPL>
 struct RollShape {
     static constexpr bool two = NW * RPL <= 2 || NW * RPL > 4;
-    static constexpr int nb_light = NW * RPL <= 2 ? 2 : 3, cps_light = NW * RPL > 4 ? 2 : 0;   // cps 0: occupancy - 1
+    static constexpr int nb_light = NW * RPL <= 2 ? 2 : 3, cps_light = NW * RPL > 4 ? 2 : (NW * RPL <= 2 ? 3 : 0);   // cps 0: by occupancy
     static constexpr int nb_heavy = NW * RPL <= 2 ? 6 : (NW * RPL > 4 ? 5 : 3), cps_heavy = NW * RPL > 4 ? 1 : 0;
     static constexpr int heavy_pct = NW * RPL <= 2 ? 15 : 8;   // searches per 100 turns from which the heavy shape runs
 };
@@ -151,7 +154,7 @@ struct RollShape {
 template <int NW, int RPL, int OBS, int MODE>
 static int launch_shape(const DevCfg &dc, const RollArgs &ra, unsigned *order, cudaStream_t st) {
 #ifdef AGV_ROLL_NB
-    return launch_rollout<NW, RPL, OBS, 32, AGV_ROLL_NB, MODE>(dc, ra, order, st);
+    return launch_rollout<NW, RPL, OBS, AGV_ROLL_SPW, AGV_ROLL_NB, MODE>(dc, ra, order, st);
 #else
     using S = RollShape<NW, RPL>;
     if (S::two) {
@@ -165,9 +168,9 @@ static int launch_shape(const DevCfg &dc, const RollArgs &ra, unsigned *order, c
         }
         const int shape_env = env_int("AGV_ROLLOUT_SHAPE", 0);
         if (shape_env ? shape_env == 2 : heavy)
-            return launch_rollout<NW, RPL, OBS, 32, S::nb_heavy, MODE>(dc, ra, order, st, S::cps_heavy);
+            return launch_rollout<NW, RPL, OBS, AGV_ROLL_SPW, S::nb_heavy, MODE>(dc, ra, order, st, S::cps_heavy);
     }
-    return launch_rollout<NW, RPL, OBS, 32, S::nb_light, MODE>(dc, ra, order, st, S::cps_light);
+    return launch_rollout<NW, RPL, OBS, AGV_ROLL_SPW, S::nb_light, MODE>(dc, ra, order, st, S::cps_light);
 #endif
 }
 

@@ -20,6 +20,7 @@
 // Results are bit-identical to n_ticks calls of agv_tick (tests/test_gpu_rollout.py).
 #pragma once
 #include "agv_async.cuh"
+#include <cstddef>
 
 namespace agv {
 
@@ -87,7 +88,9 @@ struct RollShared {
     unsigned enc_head[2], enc_tail[2];
     uint4 enc_ring[2][ROLL_RING];          // {first record of the scene-tick, acted lo, acted hi, -}
     unsigned long long recbits[64][3];     // writer staging: the 147-bit strings of one scene-tick's records
+    uint4 lut[256];                        // 8 bits -> 8 bf16 (0.0 / 1.0): the writer's expansion is one 16-byte load
 };
+static_assert(offsetof(RollShared, enc_ring) % 16 == 0 && offsetof(RollShared, lut) % 16 == 0, "RollShared layout");
 
 constexpr int LS_IDLE = 4, LS_NEWTICK = 5, LS_TICKEND = 6;
 #ifndef AGV_ROLL_LIGHT_BFS
@@ -254,7 +257,10 @@ __device__ __forceinline__ void roll_worker(const DevCfg &c, const RollArgs &ra,
         unsigned m = __ballot_sync(FULL, s == 1u || s == 4u);
         if (!m) {
             if (*vexit) return;
-            // BFS round trips are the critical path of the heavy scenes only: quick wake-ups while the CTA has any
+            // BFS round trips are the critical path of the heavy scenes only: quick wake-ups while the CTA has any.
+            // (These polls are 12 % of the kernel's instructions.  A one-word poll -- a counter of posted requests kept
+            // by the scene warps -- halves them and was measured 1.5 % SLOWER: the ballot + atomic it adds to every
+            // scene-warp iteration costs more than the idle warps' instructions, which nothing is waiting for.)
             __nanosleep(*reinterpret_cast<volatile unsigned *>(&sh->heavy_live) ? AGV_ROLL_WORKER_FAST_NS : AGV_ROLL_WORKER_NS);
             continue;
         }
@@ -351,14 +357,7 @@ static __device__ __noinline__ void roll_expand(int vec_ok, RollShared *sh, uint
         unsigned long long lo = sh->recbits[r][wi] >> sft;
         if (sft && wi < 2u) lo |= sh->recbits[r][wi + 1] << (64u - sft);
         // (bits past the end of record r are bits 0..6 of record r+1's first channel: always zero)
-        const unsigned bits = (unsigned)lo & 0xFFu;
-        uint4 o;
-        unsigned u, w;
-        u = bits & 3u;        w = (u | (u << 15)) & 0x10001u; o.x = w * (unsigned)BF16_ONE;
-        u = (bits >> 2) & 3u; w = (u | (u << 15)) & 0x10001u; o.y = w * (unsigned)BF16_ONE;
-        u = (bits >> 4) & 3u; w = (u | (u << 15)) & 0x10001u; o.z = w * (unsigned)BF16_ONE;
-        u = (bits >> 6) & 3u; w = (u | (u << 15)) & 0x10001u; o.w = w * (unsigned)BF16_ONE;
-        d4[v] = o;
+        d4[v] = sh->lut[(unsigned)lo & 0xFFu];
     }
     __syncwarp();
 }
@@ -702,6 +701,8 @@ __device__ __forceinline__ void roll_scene_warp(const DevCfg &c, const RollArgs 
             }
             const unsigned pk = (unsigned)sx | ((unsigned)sy << 7) | ((unsigned)tx << 14) | ((unsigned)ty << 21) |
                                 ((unsigned)a.loaded << 28) | (om ? (1u << 29) : 0u);
+            // (Posting the heavy warp's request BEFORE its row DP, and cancelling or orphaning it when the DP answers,
+            // was measured: -3 % guided, -11 % in A_star mode -- the orphans take the workers from real searches.)
             // (Letting the heavy warp run one pending search itself -- no hand-off -- was measured: -15 %; its other
             // scenes, whose answers are ready, then wait for that search.)
             if (want_bfs) {  // by a worker warp; this scene waits, the others go on
@@ -752,6 +753,16 @@ __device__ __forceinline__ void rollout_cta(const DevCfg &c, const RollArgs &ra,
     } else if (warp == 1) {
         LaneScene<NW, RPL, SPW, 0> ws(c, t, smem, lane, 0);
         ws.load_tables();
+    } else if (warp == 2) {
+        for (int b = lane; b < 256; b += 32) {
+            uint4 o;
+            unsigned u, w;
+            u = b & 3u;        w = (u | (u << 15)) & 0x10001u; o.x = w * (unsigned)BF16_ONE;
+            u = (b >> 2) & 3u; w = (u | (u << 15)) & 0x10001u; o.y = w * (unsigned)BF16_ONE;
+            u = (b >> 4) & 3u; w = (u | (u << 15)) & 0x10001u; o.z = w * (unsigned)BF16_ONE;
+            u = (b >> 6) & 3u; w = (u | (u << 15)) & 0x10001u; o.w = w * (unsigned)BF16_ONE;
+            sh->lut[b] = o;
+        }
     }
     __syncthreads();
     // first fill: slot j of CTA b takes entry b + j * gridDim of the longest-first order, so the long
