@@ -529,7 +529,9 @@ __device__ __forceinline__ void roll_scene_warp(const DevCfg &c, const RollArgs 
             if (st == LS_NEWTICK) {
                 // hysteresis: a scene goes to the heavy warp at AGV_HEAVY_BFS searches per tick and returns below
                 // AGV_ROLL_LIGHT_BFS (scenes around the threshold otherwise change warps every other tick, and in the
-                // light warp every BFS costs them a whole -- long -- iteration)
+                // light warp every BFS costs them a whole -- long -- iteration).  (Measured against 16 / 8: 12 / 6 and
+                // 10 / 5 -1.2 %; also sending scenes with turns + 1.5 x searches >= 70 / 80 / 90 -- the ones a launch ends
+                // on: 64 turns and 15-20 searches a tick in the light warp -- to the heavy warp: -2 / -2 / -1 %.)
                 const int w_new = n_bfs >= (unsigned)(which ? AGV_ROLL_LIGHT_BFS : AGV_HEAVY_BFS) ? 1 : 0;
                 if (k >= K) {          // this scene is through: a worker stores it and fetches the next one
                     ws.regs_to_hdr(); ws.hdr_w[6] = n_bfs | (n_turns << 16);
