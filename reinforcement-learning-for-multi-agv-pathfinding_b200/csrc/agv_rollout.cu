@@ -130,9 +130,9 @@ static int launch_rollout(const DevCfg &dc, RollArgs ra, unsigned *order, cudaSt
 // shapes per map class, picked per launch by the load of every scene's last tick -- searches per 100 turns,
 // summed by the previous launch's order kernel into pinned host memory (a hint: the schedule never changes a
 // result).  Measured, AGV-steps/s (light / heavy shape):
-//   64 x 64 (c3, 16 ticks), light = 2 workers x 3 CTAs, heavy = 6 x 3:
+//   64 x 64 (c3, 16 ticks), light = 2 workers x 3 CTAs, heavy = 6 x 2 (9 warps x 92 registers fit twice):
 //       guided rollout (7 searches per 100 turns)        1.18e9 / 0.91e9     (4 x 3: 1.16e9, 3 x 3: 1.13e9)
-//       A_star control mode (all AGVs act, congested)    4.41e8 / 6.06e8     (4 x 3: 5.7e8, 6 x 2: 6.0e8, 8 x 3: 5.7e8)
+//       A_star control mode (all AGVs act, congested)    4.41e8 / 6.06e8     (4 x 3: 5.7e8, 5 x 2: 5.7e8, 8 x 2: 5.2e8)
 //   128 x 128 (c5, 8 ticks; 4 rows x 2 words per lane, 144 registers, 91 KB shared memory per CTA),
 //   light = 3 x 2, heavy = 5 x 1 (8 warps x 144 registers do not fit twice):
 //       Expert collection 128 ticks after Scene.init (4 per 100)   3.49e8 / 2.17e8
