@@ -775,6 +775,10 @@ __device__ __forceinline__ void rollout_cta(const DevCfg &c, const RollArgs &ra,
         else if (lane == 0) atomicAdd(&sh->done_slots, 1u);
     }
     __syncthreads();
+    // (More heavy scene warps per CTA -- heavy warp 1 + slot % n, so that the congested scenes a launch ends on share
+    // their warp with fewer others -- were measured: 2 -> -18 %, 3 -> -21 % guided, -4 / -15 % in A_star mode.  An
+    // iteration costs a warp the same for one active lane as for 32; every additional scene warp that runs takes
+    // that much issue / ALU-pipe time from the light warp, which carries most of the work.)
     // Role by warp index.  The SM sub-partition's arbiter is reported to pick the eligible warp with the highest
     // warp id first, so the scene warps -- whose dependent instruction chains are the critical path of every
     // scene -- get the highest ids of the CTA, the BFS workers and the record writer (throughput work with
