@@ -167,8 +167,11 @@ static int launch_shape(const DevCfg &dc, const RollArgs &ra, unsigned *order, c
             if (dump) fprintf(stderr, "agv rollout load: %llu searches / %llu turns in the scenes' last ticks -> %s\n", n_bfs, n_turns, heavy ? "heavy" : "light");
         }
         const int shape_env = env_int("AGV_ROLLOUT_SHAPE", 0);
-        if (shape_env ? shape_env == 2 : heavy)
-            return launch_rollout<NW, RPL, OBS, AGV_ROLL_SPW, S::nb_heavy, MODE>(dc, ra, order, st, S::cps_heavy);
+        if (shape_env ? shape_env == 2 : heavy) {
+            RollArgs rh = ra;
+            rh.heavy_bfs = 16; rh.light_bfs = 8;   // (agv_rollout.cuh: AGV_ROLL_HEAVY_BFS)
+            return launch_rollout<NW, RPL, OBS, AGV_ROLL_SPW, S::nb_heavy, MODE>(dc, rh, order, st, S::cps_heavy);
+        }
     }
     return launch_rollout<NW, RPL, OBS, AGV_ROLL_SPW, S::nb_light, MODE>(dc, ra, order, st, S::cps_light);
 #endif

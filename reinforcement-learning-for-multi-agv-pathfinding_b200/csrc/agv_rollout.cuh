@@ -50,6 +50,7 @@ struct RollArgs {
     LaneArgs la;              // proto / policy / obs kind, tick-0 base pointers, shared-memory plan
     int K;                    // ticks per scene
     int vec_ok;               // N % 8 == 0 and 16-byte aligned rings: vector-store path
+    int heavy_bfs, light_bfs; // searches per tick from which a scene runs on the heavy warp / below which it returns
     // per-turn records of the scene lanes, unpacked by the record writer when the scene-tick is over:
     // scr_turn [K*E*N] {wm | tpos << 49, reward f32 | plen << 32 | action << 48 | done << 56}
     // (wm = 49-bit window of matrix (b) before the move), scr_next [K*E*N] wm | tpos << 49 after the move
@@ -93,8 +94,18 @@ struct RollShared {
 static_assert(offsetof(RollShared, enc_ring) % 16 == 0 && offsetof(RollShared, lut) % 16 == 0, "RollShared layout");
 
 constexpr int LS_IDLE = 4, LS_NEWTICK = 5, LS_TICKEND = 6;
+// A scene runs on the heavy warp from AGV_ROLL_HEAVY_BFS searches in its last tick and returns to the light warp
+// below AGV_ROLL_LIGHT_BFS.  The heavy warp buys its few scenes short BFS round trips, but an iteration costs a
+// warp the same for one active lane as for 32, so every scene on it is paid for by the light warps -- measured
+// at c3 (guided, AGV-steps/s): 16 / 8: 1.19e9, 24 / 12: 1.24e9, 32 / 16: 1.27e9, 40 / 20: 1.28e9, 40 / 30: 1.29e9,
+// 48 / 24: 1.26e9, 64 / 32: 1.24e9, no heavy scenes at all: 1.24e9.  In the congested modes (heavy launch shape, 6
+// workers) the searches bind and the old 16 / 8 is better: c3 A_star control mode 6.0e8 against 5.6e8 with 40 / 30.
+// (RollArgs::heavy_bfs / light_bfs, set per launch shape in agv_rollout.cu.)
+#ifndef AGV_ROLL_HEAVY_BFS
+#define AGV_ROLL_HEAVY_BFS 40
+#endif
 #ifndef AGV_ROLL_LIGHT_BFS
-#define AGV_ROLL_LIGHT_BFS 8
+#define AGV_ROLL_LIGHT_BFS 30
 #endif
 #ifndef AGV_ROLL_SLOW_EVERY
 #define AGV_ROLL_SLOW_EVERY 1   // power of two: the light scene warp runs its slow section every n-th iteration
@@ -201,7 +212,7 @@ __device__ __forceinline__ void roll_store_slot(const DevCfg &c, const LaneArgs 
 // loads scene e into `slot`, builds its occupancy rows and hands it to the scene warp that fits its weight
 template <int NW>
 __device__ __forceinline__ void roll_load_slot(const DevCfg &c, const LaneArgs &t, uint8_t *smem, RollShared *sh,
-                                               int slot, int e, int lane) {
+                                               int slot, int e, int lane, int heavy_bfs) {
     constexpr int WB = 64 * NW;
     const int wps = c.env_stride >> 2, HN = c.H * NW;
     const uint32_t *src = reinterpret_cast<const uint32_t *>(c.state + (size_t)e * c.env_stride);
@@ -235,7 +246,7 @@ __device__ __forceinline__ void roll_load_slot(const DevCfg &c, const LaneArgs &
         sh->slot_e[slot] = e;
         sh->slot_k[slot] = 0;
         sh->slot_fl[slot] = bits != n_created ? 1u : 0u;
-        const unsigned heavy = (blk[6] & 0xFFFFu) >= (unsigned)AGV_HEAVY_BFS ? 1u : 0u;
+        const unsigned heavy = (blk[6] & 0xFFFFu) >= (unsigned)heavy_bfs ? 1u : 0u;
         __threadfence_block();
         *reinterpret_cast<volatile unsigned *>(&sh->ctl[slot]) = 2u + heavy;
     }
@@ -296,7 +307,7 @@ __device__ __forceinline__ void roll_worker(const DevCfg &c, const RollArgs &ra,
             __syncwarp();
             if (lane == 0) vs[j] = 0u;
             if (idx < (unsigned)c.E) {
-                roll_load_slot<NW>(c, t, smem, sh, j, (int)__ldg(ra.order + idx), lane);
+                roll_load_slot<NW>(c, t, smem, sh, j, (int)__ldg(ra.order + idx), lane, ra.heavy_bfs);
             } else if (lane == 0) {
                 sh->slot_e[j] = -1;
                 *reinterpret_cast<volatile unsigned *>(&sh->ctl[j]) = 4u;
@@ -527,12 +538,12 @@ __device__ __forceinline__ void roll_scene_warp(const DevCfg &c, const RollArgs 
             }
             // ---- start of a tick
             if (st == LS_NEWTICK) {
-                // hysteresis: a scene goes to the heavy warp at AGV_HEAVY_BFS searches per tick and returns below
+                // hysteresis: a scene goes to the heavy warp at AGV_ROLL_HEAVY_BFS searches per tick and returns below
                 // AGV_ROLL_LIGHT_BFS (scenes around the threshold otherwise change warps every other tick, and in the
                 // light warp every BFS costs them a whole -- long -- iteration).  (Measured against 16 / 8: 12 / 6 and
                 // 10 / 5 -1.2 %; also sending scenes with turns + 1.5 x searches >= 70 / 80 / 90 -- the ones a launch ends
                 // on: 64 turns and 15-20 searches a tick in the light warp -- to the heavy warp: -2 / -2 / -1 %.)
-                const int w_new = n_bfs >= (unsigned)(which ? AGV_ROLL_LIGHT_BFS : AGV_HEAVY_BFS) ? 1 : 0;
+                const int w_new = n_bfs >= (unsigned)(which ? ra.light_bfs : ra.heavy_bfs) ? 1 : 0;
                 if (k >= K) {          // this scene is through: a worker stores it and fetches the next one
                     ws.regs_to_hdr(); ws.hdr_w[6] = n_bfs | (n_turns << 16);
                     __threadfence_block();
@@ -771,7 +782,7 @@ __device__ __forceinline__ void rollout_cta(const DevCfg &c, const RollArgs &ra,
     // scenes are spread over all CTAs; later scenes come from the queue counter (starts at SPW * gridDim)
     for (int j = warp; j < SPW; j += n_warps) {
         const unsigned idx = blockIdx.x + (unsigned)j * gridDim.x;
-        if (idx < (unsigned)c.E) roll_load_slot<NW>(c, t, smem, sh, j, (int)__ldg(ra.order + idx), lane);
+        if (idx < (unsigned)c.E) roll_load_slot<NW>(c, t, smem, sh, j, (int)__ldg(ra.order + idx), lane, ra.heavy_bfs);
         else if (lane == 0) atomicAdd(&sh->done_slots, 1u);
     }
     __syncthreads();
