@@ -9,11 +9,21 @@ namespace agv {
 void note_launch();
 void note_cuda_error(int e);
 
-template <int NW, int RPL>
-constexpr int rollout_min_ctas() { return NW * RPL <= 2 ? 4 : (NW * RPL <= 4 ? 2 : 1); }
+// Resident CTAs the register allocation has to leave room for.  The <= 64 x 64 kernels run 2 CTAs per SM (launch
+// shapes below); compiled for 4 they got 80 registers with 3 workers -- and 56 with 6, spilling.  Measured at c3
+// with 3 workers: room for 4 CTAs (80 registers) 1.34e9 guided / 1.24e9 with per-AGV actions, for 3 (96 registers)
+// 1.41e9 / 1.33e9, for 2 (108 registers, the compiler's own choice) 1.38e9 / 1.35e9.
+#ifndef AGV_ROLL_MINCTAS
+#define AGV_ROLL_MINCTAS 0
+#endif
+template <int NW, int RPL, int NB, int MODE>
+constexpr int rollout_min_ctas() {
+    return (NW == 1 && RPL <= 2) ? (AGV_ROLL_MINCTAS ? AGV_ROLL_MINCTAS : (NB >= 4 || MODE == 3 || MODE == 0 ? 2 : 3))
+                         : (NW * RPL <= 4 ? 2 : 1);
+}
 
 template <int NW, int RPL, int OBS, int SPW, int NB, int MODE>
-__global__ void __launch_bounds__(32 * (3 + NB), rollout_min_ctas<NW, RPL>())
+__global__ void __launch_bounds__(32 * (3 + NB), rollout_min_ctas<NW, RPL, NB, MODE>())
 k_rollout(const DevCfg c, const RollArgs ra) {
     extern __shared__ __align__(16) uint8_t lane_smem[];
     rollout_cta<NW, RPL, OBS, SPW, NB, MODE>(c, ra, lane_smem);
@@ -130,25 +140,35 @@ static int launch_rollout(const DevCfg &dc, RollArgs ra, unsigned *order, cudaSt
 // shapes per map class, picked per launch by the load of every scene's last tick -- searches per 100 turns,
 // summed by the previous launch's order kernel into pinned host memory (a hint: the schedule never changes a
 // result).  Measured, AGV-steps/s (light / heavy shape):
-//   64 x 64 (c3, 16 ticks), light = 2 workers x 3 CTAs, heavy = 6 x 2 (9 warps x 92 registers fit twice):
-//       guided rollout (7 searches per 100 turns)        1.18e9 / 0.91e9     (4 x 3: 1.16e9, 3 x 3: 1.13e9)
-//       A_star control mode (all AGVs act, congested)    4.41e8 / 6.06e8     (4 x 3: 5.7e8, 5 x 2: 5.7e8, 8 x 2: 5.2e8)
+//   64 x 64 (c3, 16 ticks), light = 3 workers x 2 CTAs, heavy = 8 x 2:
+//       guided rollout (10 searches per 100 turns)       1.41e9 / 0.95e9     (2 x 3: 1.28e9, 3 x 3: 1.17e9, 2 x 2:
+//                                                         1.05e9, 4 x 2: 1.23e9, 4 x 1: 1.07e9)
+//       A_star control mode (54 per 100)                 4.4e8 / 6.6e8       (heavy with 6 workers: 6.3e8, 10: 6.7e8)
 //   128 x 128 (c5, 8 ticks; 4 rows x 2 words per lane, 144 registers, 91 KB shared memory per CTA),
 //   light = 3 x 2, heavy = 5 x 1 (8 warps x 144 registers do not fit twice):
 //       Expert collection 128 ticks after Scene.init (4 per 100)   3.49e8 / 2.17e8
 //       stationary guided rollout (11 per 100)                      2.29e8 / 2.46e8
 //       stationary A_star control mode (22 per 100)                 1.61e8 / 1.91e8
+// WHERE the warps land matters as much as how many there are: the hardware gives a CTA consecutive warp slots and
+// slot % 4 is the SM sub-partition (tuning/micro/placement.cu prints %smid / %warpid: CTAs b and b + 148 share an
+// SM, the second one starts at the next free slot).  Two 6-warp CTAs put {worker, heavy, worker}, {worker, LIGHT,
+// writer}, {worker, worker, heavy}, {writer, worker, LIGHT} on the four sub-partitions.  The same twelve warps
+// padded to 8-warp CTAs (both light warps meet two workers each): 1.10e9; light warps kept clear of every worker,
+// the six workers on two sub-partitions: 1.21e9; the natural 6-warp layout: 1.34e9.
 // Map classes in between (64 x 128, 128 x 64) run 3 workers; AGV_ROLL_NB fixes the worker count (tuning builds),
 // AGV_ROLLOUT_SHAPE=1|2 forces light | heavy (tests), AGV_ROLLOUT_CPS the CTAs per SM.
 #ifndef AGV_ROLL_SPW
 #define AGV_ROLL_SPW 32   // scene slots per CTA = lanes of a scene warp in use (tuning builds: 16)
 #endif
+#ifndef AGV_ROLL_NB_HEAVY
+#define AGV_ROLL_NB_HEAVY 8   // workers per CTA of the <= 64 x 64 heavy shape
+#endif
 template <int NW, int RPL>
 struct RollShape {
-    static constexpr bool two = NW * RPL <= 2 || NW * RPL > 4;
-    static constexpr int nb_light = NW * RPL <= 2 ? 2 : 3, cps_light = NW * RPL > 4 ? 2 : (NW * RPL <= 2 ? 3 : 0);   // cps 0: by occupancy
-    static constexpr int nb_heavy = NW * RPL <= 2 ? 6 : (NW * RPL > 4 ? 5 : 3), cps_heavy = NW * RPL > 4 ? 1 : 0;
-    static constexpr int heavy_pct = NW * RPL <= 2 ? 15 : 8;   // searches per 100 turns from which the heavy shape runs
+    static constexpr bool two = (NW == 1 && RPL <= 2) || NW * RPL > 4;
+    static constexpr int nb_light = 3, cps_light = NW * RPL > 4 || (NW == 1 && RPL <= 2) ? 2 : 0;   // cps 0: by occupancy
+    static constexpr int nb_heavy = (NW == 1 && RPL <= 2) ? AGV_ROLL_NB_HEAVY : (NW * RPL > 4 ? 5 : 3), cps_heavy = NW * RPL > 4 ? 1 : 0;
+    static constexpr int heavy_pct = (NW == 1 && RPL <= 2) ? 15 : 8;   // searches per 100 turns from which the heavy shape runs
 };
 
 template <int NW, int RPL, int OBS, int MODE>
