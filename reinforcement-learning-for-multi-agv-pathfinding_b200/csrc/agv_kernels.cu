@@ -514,7 +514,7 @@ static int rollout_launch(AgvHandle *h, int n_ticks, int proto, int policy, int 
     la.plen = plen_dev; la.slen = slen_dev; la.obs = (uint16_t *)obs_dev; la.next_obs = (uint16_t *)next_obs_dev;
     la.rec_elems = obs_elems(h, obs_kind);
     ra.K = n_ticks;
-    ra.heavy_bfs = AGV_ROLL_HEAVY_BFS; ra.light_bfs = AGV_ROLL_LIGHT_BFS;
+    ra.heavy_bfs = ra.light_bfs = -1;   // per map class and launch shape (agv_rollout.cu: launch_shape)
     ra.scr_turn = reinterpret_cast<ulonglong2 *>(h->d_scr[0]); ra.scr_next = h->d_scr[1];
     ra.qctr = h->d_qctr;
     ra.stat = h->h_rstat;  // (unified addressing: the pinned host pointer is valid on the device)

@@ -136,26 +136,27 @@ static int launch_rollout(const DevCfg &dc, RollArgs ra, unsigned *order, cudaSt
 //
 // Launch shape = BFS worker warps per CTA x CTAs per SM.  The best shape depends on how many turns need the
 // level-synchronous BFS (the row DP decides the others inside the scene warp): with few searches the scene
-// warps' turn chains bind and idle workers only compete for issue slots; with many, the searches bind.  Two
-// shapes per map class, picked per launch by the load of every scene's last tick -- searches per 100 turns,
+// warps' turn chains bind and idle workers only compete for issue slots; with many, the searches bind.  Maps
+// up to 64 x 64 have two shapes, picked per launch by the load of every scene's last tick -- searches per 100 turns,
 // summed by the previous launch's order kernel into pinned host memory (a hint: the schedule never changes a
 // result).  Measured, AGV-steps/s (light / heavy shape):
 //   64 x 64 (c3, 16 ticks), light = 3 workers x 2 CTAs, heavy = 8 x 2:
 //       guided rollout (10 searches per 100 turns)       1.41e9 / 0.95e9     (2 x 3: 1.28e9, 3 x 3: 1.17e9, 2 x 2:
 //                                                         1.05e9, 4 x 2: 1.23e9, 4 x 1: 1.07e9)
 //       A_star control mode (54 per 100)                 4.4e8 / 6.6e8       (heavy with 6 workers: 6.3e8, 10: 6.7e8)
-//   128 x 128 (c5, 8 ticks; 4 rows x 2 words per lane, 144 registers, 91 KB shared memory per CTA),
-//   light = 3 x 2, heavy = 5 x 1 (8 warps x 144 registers do not fit twice):
-//       Expert collection 128 ticks after Scene.init (4 per 100)   3.49e8 / 2.17e8
-//       stationary guided rollout (11 per 100)                      2.29e8 / 2.46e8
-//       stationary A_star control mode (22 per 100)                 1.61e8 / 1.91e8
+//   128 x 128 (c5, 8 ticks; 4 rows x 2 words per lane, 144 registers, 95 KB shared memory per CTA): one shape, 3
+//   workers x 2 CTAs and no heavy scenes: guided 3.30e8, A_star control mode 2.27e8, Expert collection 3.46e8.
+//   (2 workers x 2: 2.86e8 / 1.88e8; 4 or 5 workers fit only one CTA per SM: 2.2e8 - 2.5e8 / 1.9e8.  With scenes
+//   moved to the heavy warp from 16 searches per tick the same shape gave 2.3e8 / 1.6e8 -- that, not the worker
+//   count, was what an earlier two-shape scheme for this class worked around.)
 // WHERE the warps land matters as much as how many there are: the hardware gives a CTA consecutive warp slots and
 // slot % 4 is the SM sub-partition (tuning/micro/placement.cu prints %smid / %warpid: CTAs b and b + 148 share an
 // SM, the second one starts at the next free slot).  Two 6-warp CTAs put {worker, heavy, worker}, {worker, LIGHT,
 // writer}, {worker, worker, heavy}, {writer, worker, LIGHT} on the four sub-partitions.  The same twelve warps
 // padded to 8-warp CTAs (both light warps meet two workers each): 1.10e9; light warps kept clear of every worker,
 // the six workers on two sub-partitions: 1.21e9; the natural 6-warp layout: 1.34e9.
-// Map classes in between (64 x 128, 128 x 64) run 3 workers; AGV_ROLL_NB fixes the worker count (tuning builds),
+// Map classes in between (64 x 128, 128 x 64) run 3 workers and no heavy scenes either; AGV_ROLL_NB fixes the
+// worker count (tuning builds),
 // AGV_ROLLOUT_SHAPE=1|2 forces light | heavy (tests), AGV_ROLLOUT_CPS the CTAs per SM.
 #ifndef AGV_ROLL_SPW
 #define AGV_ROLL_SPW 32   // scene slots per CTA = lanes of a scene warp in use (tuning builds: 16)
@@ -165,18 +166,24 @@ static int launch_rollout(const DevCfg &dc, RollArgs ra, unsigned *order, cudaSt
 #endif
 template <int NW, int RPL>
 struct RollShape {
-    static constexpr bool two = (NW == 1 && RPL <= 2) || NW * RPL > 4;
+    static constexpr bool two = NW == 1 && RPL <= 2;
     static constexpr int nb_light = 3, cps_light = NW * RPL > 4 || (NW == 1 && RPL <= 2) ? 2 : 0;   // cps 0: by occupancy
-    static constexpr int nb_heavy = (NW == 1 && RPL <= 2) ? AGV_ROLL_NB_HEAVY : (NW * RPL > 4 ? 5 : 3), cps_heavy = NW * RPL > 4 ? 1 : 0;
-    static constexpr int heavy_pct = (NW == 1 && RPL <= 2) ? 15 : 8;   // searches per 100 turns from which the heavy shape runs
+    static constexpr int nb_heavy = two ? AGV_ROLL_NB_HEAVY : 3, cps_heavy = 0;
+    static constexpr int heavy_pct = 15;   // searches per 100 turns from which the heavy shape runs
 };
 
 template <int NW, int RPL, int OBS, int MODE>
-static int launch_shape(const DevCfg &dc, const RollArgs &ra, unsigned *order, cudaStream_t st) {
+static int launch_shape(const DevCfg &dc, const RollArgs &ra_in, unsigned *order, cudaStream_t st) {
+    using S = RollShape<NW, RPL>;
+    RollArgs ra = ra_in;
+    // searches per tick from which a scene runs on the heavy warp / below which it returns (agv_rollout.cuh):
+    // 32 / 24 for maps up to 64 x 64, never on larger maps (c5: 3.3e8 AGV-steps/s without heavy scenes, 2.7e8 with
+    // 24 / 16, 2.3e8 with 16 / 8); AGV_ROLL_HEAVY_BFS / AGV_ROLL_LIGHT_BFS override (tuning)
+    ra.heavy_bfs = env_int("AGV_ROLL_HEAVY_BFS", S::two ? AGV_ROLL_HEAVY_BFS : (1 << 20));
+    ra.light_bfs = env_int("AGV_ROLL_LIGHT_BFS", S::two ? AGV_ROLL_LIGHT_BFS : (1 << 20));
 #ifdef AGV_ROLL_NB
     return launch_rollout<NW, RPL, OBS, AGV_ROLL_SPW, AGV_ROLL_NB, MODE>(dc, ra, order, st);
 #else
-    using S = RollShape<NW, RPL>;
     if (S::two) {
         static bool heavy = false;  // (kept while the figure is unknown: right after agv_set_state / agv_reset)
         if (ra.stat && reinterpret_cast<volatile unsigned long long *>(ra.stat)[1] > 0) {
@@ -188,9 +195,9 @@ static int launch_shape(const DevCfg &dc, const RollArgs &ra, unsigned *order, c
         }
         const int shape_env = env_int("AGV_ROLLOUT_SHAPE", 0);
         if (shape_env ? shape_env == 2 : heavy) {
-            RollArgs rh = ra;
-            rh.heavy_bfs = 16; rh.light_bfs = 8;   // (agv_rollout.cuh: AGV_ROLL_HEAVY_BFS)
-            return launch_rollout<NW, RPL, OBS, AGV_ROLL_SPW, S::nb_heavy, MODE>(dc, rh, order, st, S::cps_heavy);
+            // congested launches: the searches bind, quick round trips for the scenes with many of them pay
+            ra.heavy_bfs = env_int("AGV_ROLL_HEAVY_BFS", 16); ra.light_bfs = env_int("AGV_ROLL_LIGHT_BFS", 8);
+            return launch_rollout<NW, RPL, OBS, AGV_ROLL_SPW, S::nb_heavy, MODE>(dc, ra, order, st, S::cps_heavy);
         }
     }
     return launch_rollout<NW, RPL, OBS, AGV_ROLL_SPW, S::nb_light, MODE>(dc, ra, order, st, S::cps_light);

@@ -97,15 +97,16 @@ constexpr int LS_IDLE = 4, LS_NEWTICK = 5, LS_TICKEND = 6;
 // A scene runs on the heavy warp from AGV_ROLL_HEAVY_BFS searches in its last tick and returns to the light warp
 // below AGV_ROLL_LIGHT_BFS.  The heavy warp buys its few scenes short BFS round trips, but an iteration costs a
 // warp the same for one active lane as for 32, so every scene on it is paid for by the light warps -- measured
-// at c3 (guided, AGV-steps/s): 16 / 8: 1.19e9, 24 / 12: 1.24e9, 32 / 16: 1.27e9, 40 / 20: 1.28e9, 40 / 30: 1.29e9,
-// 48 / 24: 1.26e9, 64 / 32: 1.24e9, no heavy scenes at all: 1.24e9.  In the congested modes (heavy launch shape, 6
-// workers) the searches bind and the old 16 / 8 is better: c3 A_star control mode 6.0e8 against 5.6e8 with 40 / 30.
-// (RollArgs::heavy_bfs / light_bfs, set per launch shape in agv_rollout.cu.)
+// at c3 (guided, AGV-steps/s; 2 workers x 3 CTAs per SM): 16 / 8: 1.19e9, 24 / 12: 1.24e9, 32 / 16: 1.27e9, 40 / 30:
+// 1.29e9, 64 / 32: 1.24e9, none: 1.24e9; with the final shape (3 workers x 2 CTAs, 96 registers): 32 / 24: 1.415e9
+// (e2e 1.29e9), 40 / 30: 1.40e9 (1.25e9), 64 / 48 and none: 1.33e9.  In the congested modes (heavy launch shape) the
+// searches bind and 16 / 8 is better: c3 A_star control mode 6.6e8 against 6.3e8 with 40 / 30.  On 128 x 128 maps the
+// heavy warp never pays (launch_shape in agv_rollout.cu sets RollArgs::heavy_bfs / light_bfs per class and shape).
 #ifndef AGV_ROLL_HEAVY_BFS
-#define AGV_ROLL_HEAVY_BFS 40
+#define AGV_ROLL_HEAVY_BFS 32
 #endif
 #ifndef AGV_ROLL_LIGHT_BFS
-#define AGV_ROLL_LIGHT_BFS 30
+#define AGV_ROLL_LIGHT_BFS 24
 #endif
 #ifndef AGV_ROLL_SLOW_EVERY
 #define AGV_ROLL_SLOW_EVERY 1   // power of two: the light scene warp runs its slow section every n-th iteration
