@@ -6,7 +6,7 @@ lib = os.path.join(root, "reinforcement-learning-for-multi-agv-pathfinding_b200"
 d = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=d, stdout=subprocess.DEVNULL)
 dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(d, "agv_rollout.sm_100a.cubin")], capture_output=True, text=True).stdout
-print("global stores of k_rollout<1,2,OBS_CLIP,32,2,MODE 1> and its out-of-line record expander (roll_expand), by source line")
+print("global stores of k_rollout<1,2,OBS_CLIP,32,3,MODE 1> and its out-of-line record expander (roll_expand), by source line")
 print("(cuobjdump / nvdisasm -g of the in-tree libagv_b200.so; the observation path = agv_rollout.cuh roll_expand: STG.E.128 only,")
 print(" plus the per-record fallback expand_clip7 (agv_lanes.cuh) that runs only when N % 8 != 0)\n")
 src_cache = {}
@@ -21,7 +21,7 @@ def src(path, line):
 on, cur, seen, order = False, ("?", 0), collections.Counter(), []
 for ln in dis.splitlines():
     if ln.startswith("//---") and ".text." in ln:
-        on = ("k_rolloutILi1ELi2ELi1ELi32ELi2ELi1E" in ln) or ("roll_expand" in ln)
+        on = ("k_rolloutILi1ELi2ELi1ELi32ELi3ELi1E" in ln) or ("roll_expand" in ln)
         continue
     if not on:
         continue
