@@ -403,6 +403,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scenes", type=int, default=0, help="override scenes per GPU")
+    ap.add_argument("--agvs", type=int, default=0, help="override AGVs per scene (tuning)")
     ap.add_argument("--ticks", type=int, default=16, help="ticks per step (one agv_rollout launch); 0 = one agv_tick per step")
     ap.add_argument("--reps", type=int, default=5, help="repetitions of every timed window (the median is reported)")
     ap.add_argument("--spinup", type=int, default=-1,
@@ -432,6 +433,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     gridf, N, E_default, desc = WORKLOADS[args.workload]
+    if args.agvs > 0:  # tuning: other congestion levels on the same layout
+        N = args.agvs
+        desc += " [AGVs per scene overridden: %d]" % N
     E = args.scenes or E_default
     grid = gridf()
     H, W = grid.shape
