@@ -154,7 +154,9 @@ static int launch_rollout(const DevCfg &dc, RollArgs ra, unsigned *order, cudaSt
 // SM, the second one starts at the next free slot).  Two 6-warp CTAs put {worker, heavy, worker}, {worker, LIGHT,
 // writer}, {worker, worker, heavy}, {writer, worker, LIGHT} on the four sub-partitions.  The same twelve warps
 // padded to 8-warp CTAs (both light warps meet two workers each): 1.10e9; light warps kept clear of every worker,
-// the six workers on two sub-partitions: 1.21e9; the natural 6-warp layout: 1.34e9.
+// the six workers on two sub-partitions: 1.21e9; the natural 6-warp layout: 1.34e9.  (With the final register
+// budget: natural 1.41e9; each light warp with exactly one worker and nothing else, roles taken from %warpid:
+// 1.06e9 -- every 8-warp arrangement tried lost 15-25 %, so slot % 4 is at best part of the story.)
 // Map classes in between (64 x 128, 128 x 64) run 3 workers and no heavy scenes either; AGV_ROLL_NB fixes the
 // worker count (tuning builds),
 // AGV_ROLLOUT_SHAPE=1|2 forces light | heavy (tests), AGV_ROLLOUT_CPS the CTAs per SM.
