@@ -143,8 +143,9 @@ int agv_tick_host_join(AgvHandle *h, void *stream);
  * scheduled longest-first (by the turns + BFS searches of their last tick) onto persistent CTAs; long
  * rollouts are taken 16 ticks per launch.  Inside a written group of 8 observation records, records of AGVs
  * without a turn are zero-filled; mask with act_out >= 0 as for agv_tick.  Configurations the persistent
- * kernel does not cover (shaped reward, full-map observations, K != 7) and maps up to 32 rows x 64 columns
- * (where the warp-per-scene tick is faster) run as n_ticks fused ticks inside this call -- same results. */
+ * kernel does not cover (shaped reward, full-map observations, K != 7) run as n_ticks fused ticks inside this
+ * call; maps up to 32 rows x 64 columns run on the warp-per-scene kernel, which keeps every scene in its warp
+ * for all n_ticks (one launch) -- same results. */
 int agv_rollout(AgvHandle *h, int32_t n_ticks, int32_t proto, int32_t policy, int32_t obs_kind,
                 const int8_t *action_dev, int8_t *act_out_dev, float *reward_dev, uint8_t *done_dev,
                 uint16_t *plen_dev, uint16_t *slen_dev, void *obs_dev, void *next_obs_dev, void *stream);

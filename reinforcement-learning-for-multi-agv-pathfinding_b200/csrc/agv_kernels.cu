@@ -70,7 +70,11 @@ constexpr int tick_min_blocks() {
 #ifndef AGV_TICK_MINB8
 #define AGV_TICK_MINB8 2  // 8 u64 per lane (128 x 128)
 #endif
-    return NW * RPL <= 2 ? AGV_TICK_MINB : (NW * RPL <= 4 ? AGV_TICK_MINB4 : AGV_TICK_MINB8);
+#ifndef AGV_TICK_MINB1
+#define AGV_TICK_MINB1 7  // 1 u64 per lane (maps up to 32 rows x 64 columns): 72 registers, no spills -- 28 one-warp CTAs per SM,
+                          // 4096 scenes are one wave on 148 SMs (README 9x9, 4096 scenes: 5.08e8 -> 5.65e8 AGV-steps/s)
+#endif
+    return NW * RPL <= 1 ? AGV_TICK_MINB1 : NW * RPL <= 2 ? AGV_TICK_MINB : (NW * RPL <= 4 ? AGV_TICK_MINB4 : AGV_TICK_MINB8);
 }
 
 template <int NW, int RPL, int OBS, bool SHAPED>
@@ -163,6 +167,111 @@ __global__ void __launch_bounds__(128, tick_min_blocks<NW, RPL>()) k_tick(const 
         if (t.plen) t.plen[rec] = o_plen[j];
         if (t.slen) t.slen[rec] = o_slen[j];
     }
+}
+
+// Small maps (up to 32 rows x 64 columns, one u64 per lane): the same tick with the loop over n_ticks INSIDE the
+// launch -- a tick of the README 9x9 scene is launch-sized (24 us for 4096 scenes), so the scene stays in its warp
+// and the outputs advance by E * N records per tick.  A separate kernel with its own n_ticks parameter on purpose:
+// four more bytes in TickArgs changed the register allocation of every k_tick instance (8 -> 40 bytes of spills in
+// the HBM-bound full-map encode at 64 x 64, -3 %).
+template <int NW, int RPL, int OBS, bool SHAPED>
+__global__ void __launch_bounds__(128, tick_min_blocks<NW, RPL>()) k_tick_small(const DevCfg c, const TickArgs t, const int n_ticks) {
+    WARP_PROLOGUE(t)
+    int8_t *o_act = reinterpret_cast<int8_t *>(wbase + t.off_act);
+    uint8_t *o_done = wbase + t.off_done;
+    uint16_t *o_plen = reinterpret_cast<uint16_t *>(wbase + t.off_plen);
+    uint16_t *o_slen = reinterpret_cast<uint16_t *>(wbase + t.off_slen);
+    float *o_rew = reinterpret_cast<float *>(wbase + t.off_rew);
+    uint16_t *stage = reinterpret_cast<uint16_t *>(wbase + t.off_stage);
+    uint16_t *stage2 = reinterpret_cast<uint16_t *>(wbase + t.off_stage2);
+    const int N = c.N, R = t.rec_elems, G = t.group;
+    constexpr bool clip = OBS == OBS_CLIP, full = OBS == OBS_FULL;
+
+  const size_t tick_recs = (size_t)c.E * N;
+  for (int tk = 0; tk < n_ticks; tk++) {
+    const size_t rec0 = (size_t)tk * tick_recs + (size_t)e * N;   // first output record of this scene-tick
+    bool live = true;
+    if (ws.over) {
+        if (c.auto_reset) ws.reset();
+        else live = false;
+    }
+    if (live) { ws.build_occ(); ws.tick++; ws.acted_mask = 0; }
+    // per-AGV outputs default to "no turn"; the turn loop only visits the created prefix and
+    // stops at the first uncreated AGV (Scene.py:127-128) or when the episode is over
+    for (int j = lane; j < N; j += 32) { o_act[j] = -1; o_done[j] = 0; o_rew[j] = 0.f; o_plen[j] = 0; o_slen[j] = 0xFFFF; }
+    __syncwarp();
+    const int n_loop = live ? min(N, ws.n_created) : 0;  // spawn happens after the loop
+    const int8_t *given_row = (t.policy == POLICY_GIVEN && t.action) ? t.action + rec0 : nullptr;
+    bool group_dirty = false;
+    int i = 0;
+    for (; i < n_loop && !ws.over; i++) {
+        bool act = false;
+        if (ws.finished) {                                   // Scene.py:129-130 return
+            ws.over = 1;
+            ws.cnt_ended++;
+        } else act = !((ws.meta_s[i] >> 3) & 1);             // Scene.py:132-134 idle AGVs are skipped
+        const size_t rec = rec0 + i;
+        uint16_t *od = nullptr, *nd = nullptr;
+        if (clip) {
+            if (t.obs) od = stage + (size_t)(i & (G - 1)) * R;
+            if (t.next_obs) nd = stage2 + (size_t)(i & (G - 1)) * R;
+        } else if (full) {
+            if (t.obs) od = t.obs + rec * R;
+            if (t.next_obs) nd = t.next_obs + rec * R;
+        }
+        if (act) {
+            TurnOut o;
+            const int given = given_row ? (int)given_row[i] : -1;
+            do_turn<NW, RPL, OBS, SHAPED>(ws, i, t.proto, t.policy, given, od, nd, o);
+            // warp-uniform values, stored by every lane (no divergent lane-0 block)
+            o_act[i] = (int8_t)o.action; o_done[i] = (uint8_t)o.done; o_rew[i] = o.reward;
+            o_plen[i] = (uint16_t)o.plen; o_slen[i] = (uint16_t)o.slen;
+        } else if (clip) {
+            // no turn: observation records of this AGV are left untouched in HBM (the consumer
+            // masks with act_out >= 0); inside a flush group the slot is zero-filled so that the
+            // group still goes out as one aligned vector store
+            if (od) for (int q = lane; q < R; q += 32) od[q] = 0;
+            if (nd) for (int q = lane; q < R; q += 32) nd[q] = 0;
+        }
+        if (clip) {
+            group_dirty |= act;
+            if (((i + 1) & (G - 1)) == 0) {  // G is a power of two: group complete
+                if (group_dirty) {
+                    const size_t off = (rec0 + (i & ~(G - 1))) * R;
+                    if (t.obs) flush_bytes(reinterpret_cast<uint8_t *>(t.obs + off),
+                                           reinterpret_cast<uint8_t *>(stage), G * R * 2, lane);
+                    if (t.next_obs) flush_bytes(reinterpret_cast<uint8_t *>(t.next_obs + off),
+                                                reinterpret_cast<uint8_t *>(stage2), G * R * 2, lane);
+                }
+                group_dirty = false;
+            }
+        }
+    }
+    if (clip && group_dirty && (i & (G - 1)) != 0) {  // partially filled last group
+        const int g0 = i & ~(G - 1), nrec = i - g0;
+        const size_t off = (rec0 + g0) * R;
+        if (t.obs) flush_bytes(reinterpret_cast<uint8_t *>(t.obs + off), reinterpret_cast<uint8_t *>(stage),
+                               nrec * R * 2, lane);
+        if (t.next_obs) flush_bytes(reinterpret_cast<uint8_t *>(t.next_obs + off),
+                                    reinterpret_cast<uint8_t *>(stage2), nrec * R * 2, lane);
+    }
+    if (live && !ws.over) ws.spawn();
+    if (tk + 1 == n_ticks) {  // (before the output stores, as in the one-tick kernel: the scene's registers die here)
+        ws.regs_to_hdr();
+        ws.flush_counters();
+        ws.store_block(wbase + t.off_blk, e);
+    }
+    __syncwarp();
+    for (int j = lane; j < N; j += 32) {
+        const size_t rec = rec0 + j;
+        if (t.act_out) t.act_out[rec] = o_act[j];
+        if (t.done) t.done[rec] = o_done[j];
+        if (t.reward) t.reward[rec] = o_rew[j];
+        if (t.plen) t.plen[rec] = o_plen[j];
+        if (t.slen) t.slen[rec] = o_slen[j];
+    }
+    __syncwarp();
+  }
 }
 
 // ---------------------------------------------------------------- sub-step kernels
@@ -647,9 +756,11 @@ int agv_reset(AgvHandle *h, const uint8_t *env_mask_dev, void *stream) {
 #undef CALL
 }
 
-int agv_tick(AgvHandle *h, int32_t proto, int32_t policy, int32_t obs_kind, const int8_t *action_dev,
-             int8_t *act_out_dev, float *reward_dev, uint8_t *done_dev, uint16_t *plen_dev, uint16_t *slen_dev,
-             void *obs_dev, void *next_obs_dev, void *stream) {
+// n_ticks fused ticks in one launch: only the warp-per-scene kernel loops over ticks itself (outputs advance by
+// E * N records per tick); the lane-per-scene kernels return AGV_E_UNSUPPORTED for n_ticks > 1
+static int tick_n(AgvHandle *h, int n_ticks, int32_t proto, int32_t policy, int32_t obs_kind, const int8_t *action_dev,
+                  int8_t *act_out_dev, float *reward_dev, uint8_t *done_dev, uint16_t *plen_dev, uint16_t *slen_dev,
+                  void *obs_dev, void *next_obs_dev, void *stream) {
     if (!h || proto < 0 || proto > 1 || policy < 0 || policy > 2 || obs_kind < 0 || obs_kind > 2) return AGV_E_INVALID;
     if (obs_kind == AGV_OBS_NONE && (obs_dev || next_obs_dev)) return AGV_E_INVALID;
     CUDA_TRY(cudaSetDevice(h->cfg.device));
@@ -661,6 +772,9 @@ int agv_tick(AgvHandle *h, int32_t proto, int32_t policy, int32_t obs_kind, cons
     const int N = h->cfg.N;
     t.rec_elems = obs_elems(h, t.obs_kind);
     const int impl = tick_impl(h, t.obs_kind);
+    // (several ticks per launch pay on small maps, where a tick is launch-sized: README 9x9, 4096 scenes, 32 ticks
+    // per call 5.6e8 -> 6.7e8 AGV-steps/s; the HBM-bound full-map encode at 64 x 64 loses 2 % to the longer waves)
+    if (n_ticks != 1 && (impl > 0 || !(h->NW == 1 && h->RPL == 1))) return AGV_E_UNSUPPORTED;
     if (impl == 3) {
         const int rc = rollout_launch(h, 1, proto, policy, t.obs_kind, action_dev, act_out_dev, reward_dev, done_dev,
                                       plen_dev, slen_dev, obs_dev, next_obs_dev, (cudaStream_t)stream);
@@ -679,7 +793,7 @@ int agv_tick(AgvHandle *h, int32_t proto, int32_t policy, int32_t obs_kind, cons
             return rc;
         }  // scenes too large for a lane-per-scene warp: warp-per-scene path
     }
-    g_tick_kernel = "k_tick (warp-per-scene)";
+    g_tick_kernel = (h->NW == 1 && h->RPL == 1) ? "k_tick_small (warp-per-scene, tick loop inside the launch)" : "k_tick (warp-per-scene)";
     t.group = 1;
     if (t.obs_kind == AGV_OBS_CLIP) {
         const int rb = t.rec_elems * 2;
@@ -699,8 +813,12 @@ int agv_tick(AgvHandle *h, int32_t proto, int32_t policy, int32_t obs_kind, cons
     t.off_stage = off; off += t.obs ? stage_bytes : 0;
     t.off_stage2 = off; off += t.next_obs ? stage_bytes : 0;
     t.per_warp = off;
-#define CALL_OS(NW_, RPL_, OBS_, SH_) \
-    return launch_warps(k_tick<NW_, RPL_, OBS_, SH_>, h->cfg.E, t.per_warp, (cudaStream_t)stream, h->dc, t)
+#define CALL_OS(NW_, RPL_, OBS_, SH_)                                                                                   \
+    do {                                                                                                                \
+        if (NW_ == 1 && RPL_ == 1)                                                                                      \
+            return launch_warps(k_tick_small<1, 1, OBS_, SH_>, h->cfg.E, t.per_warp, (cudaStream_t)stream, h->dc, t, n_ticks); \
+        return launch_warps(k_tick<NW_, RPL_, OBS_, SH_>, h->cfg.E, t.per_warp, (cudaStream_t)stream, h->dc, t);        \
+    } while (0)
 #define CALL(NW_, RPL_)                                                              \
     do {                                                                             \
         const bool sh = h->cfg.shaped_reward != 0;                                   \
@@ -711,6 +829,13 @@ int agv_tick(AgvHandle *h, int32_t proto, int32_t policy, int32_t obs_kind, cons
     DISPATCH(h, CALL);
 #undef CALL
 #undef CALL_OS
+}
+
+int agv_tick(AgvHandle *h, int32_t proto, int32_t policy, int32_t obs_kind, const int8_t *action_dev,
+             int8_t *act_out_dev, float *reward_dev, uint8_t *done_dev, uint16_t *plen_dev, uint16_t *slen_dev,
+             void *obs_dev, void *next_obs_dev, void *stream) {
+    return tick_n(h, 1, proto, policy, obs_kind, action_dev, act_out_dev, reward_dev, done_dev, plen_dev, slen_dev,
+                  obs_dev, next_obs_dev, stream);
 }
 
 int agv_tick_host(AgvHandle *h, int32_t proto, int32_t policy, int32_t obs_kind, const int8_t *action_host,
@@ -795,8 +920,16 @@ int agv_rollout(AgvHandle *h, int32_t n_ticks, int32_t proto, int32_t policy, in
         }
         if (rc != AGV_E_UNSUPPORTED) return rc;
     }
-    // configurations the persistent kernel does not cover (shaped reward, full-map observations,
-    // K != 7): n_ticks launches of the fused tick, each writing its slice of the rings
+    // configurations the persistent kernel does not cover (shaped reward, full-map observations, K != 7) and
+    // small maps: the warp-per-scene kernel keeps every scene in its warp for all n_ticks (one launch) ...
+    {
+        static const bool per_tick = getenv("AGV_ROLLOUT_PER_TICK") != nullptr;   // (A/B runs)
+        const int rc = per_tick ? AGV_E_UNSUPPORTED
+                                : tick_n(h, n_ticks, proto, policy, obs_kind, action_dev, act_out_dev, reward_dev, done_dev,
+                                         plen_dev, slen_dev, obs_dev, next_obs_dev, stream);
+        if (rc != AGV_E_UNSUPPORTED) return rc;
+    }
+    // ... the lane-per-scene ticks run as n_ticks launches, each writing its slice of the rings
     for (int k = 0; k < n_ticks; k++) {
         const size_t o = per * (size_t)k;
         const int rc = agv_tick(h, proto, policy, obs_kind, action_dev ? action_dev + o : nullptr,
